@@ -1,0 +1,220 @@
+/*
+ * b2rl.h -- C ABI of libb2rl.so, the B200 (sm_100a) replay / loss hot path
+ * that sits behind pfrl_b200's PFRL-compatible Python classes.
+ *
+ * The reference (pfnet/pfrl) is pure Python and has no FFI of its own; each
+ * entry point below names the reference code it replaces (file:line relative
+ * to the reference root).  INTEGRATION.md shows the ctypes binding a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative b2rl_status on error;
+ *    b2rl_last_error() returns a thread-local message for the last failure.
+ *  - no exceptions, no Python / torch types: plain pointers and sizes.
+ *  - "dev" pointers are device pointers owned by the caller (e.g. torch
+ *    tensors); they must stay alive until `stream` has passed the call.
+ *    "host" pointers are read synchronously before the call returns.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *    stream).  All work is enqueued asynchronously on it; the library never
+ *    synchronises the device unless the function says so.
+ *  - a handle is not thread-safe (same single-caller discipline as the
+ *    reference's replay buffers).
+ */
+#ifndef B2RL_H
+#define B2RL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B2RL_OK = 0,
+    B2RL_ERR_INVALID = -1,  /* bad argument */
+    B2RL_ERR_CUDA = -2,     /* CUDA runtime error (see b2rl_last_error) */
+    B2RL_ERR_PROTOCOL = -3, /* sample / update ordering violated
+                               (asserts at collections/prioritized.py:98,108) */
+    B2RL_ERR_RANGE = -4,    /* index / size out of range */
+    B2RL_ERR_NOMEM = -5
+} b2rl_status;
+
+const char *b2rl_last_error(void);
+/* Library / build identification, e.g. "b2rl 0.1 sm_100a". */
+const char *b2rl_version(void);
+
+/* ------------------------------------------------------------------------
+ * Replay store: HBM ring of observation parts ("frames") + per-experience
+ * records + (optionally) fp64 sum / min segment trees.
+ *
+ * Replaces: pfrl/replay_buffers/replay_buffer.py:24-80 (storage of n-step
+ * experiences), pfrl/collections/random_access_queue.py:6-101,
+ * pfrl/collections/prioritized.py:21-323 (PrioritizedBuffer, SumTreeQueue,
+ * MinTreeQueue).
+ *
+ * An *observation* is `stack` parts of `part_bytes` bytes each (Atari:
+ * 4 frames of 84*84 uint8; vector obs: 1 part of 4*dim bytes).  Parts are
+ * shared between observations exactly like the reference's LazyFrames share
+ * frame arrays (pfrl/wrappers/atari_wrappers.py:251-272).
+ * An *experience* is what the reference stores as one replay element: the
+ * list of 1..n_step consecutive transitions (replay_buffer.py:52-62).  Its
+ * record holds: part slots of the first transition's state and of the last
+ * transition's next_state, the first action, the per-step rewards, the
+ * number of steps and the "any terminal" flag -- everything
+ * batch_experiences (pfrl/replay_buffer.py:157-212) reads.
+ * ---------------------------------------------------------------------- */
+typedef struct b2rl_replay b2rl_replay;
+
+typedef struct {
+    int64_t capacity;      /* max live experiences (> 0)                     */
+    int64_t part_capacity; /* slots in the part ring (>= parts kept alive)   */
+    int32_t part_bytes;    /* bytes per part; multiple of 16                 */
+    int32_t stack;         /* parts per observation (1..8)                   */
+    int32_t n_step;        /* max transitions per experience (1..8)          */
+    int32_t action_bytes;  /* bytes per action (int64 -> 8, f32[6] -> 24)    */
+    int32_t prioritized;   /* 1: keep sum/min trees                          */
+    int32_t device;        /* CUDA device ordinal                            */
+    int32_t max_batch;     /* largest sample/update batch (<= 65536)         */
+    int32_t reserved;
+} b2rl_replay_config;
+
+int b2rl_replay_create(const b2rl_replay_config *cfg, b2rl_replay **out);
+int b2rl_replay_destroy(b2rl_replay *h);
+
+/* Host mirrors of the counters (no device sync): live experiences, absolute
+ * append / pop counters (collections/prioritized.py TreeQueue.length and the
+ * popleft count). */
+int64_t b2rl_replay_len(const b2rl_replay *h);
+int64_t b2rl_replay_napp(const b2rl_replay *h);
+int64_t b2rl_replay_npop(const b2rl_replay *h);
+/* Bytes of HBM the handle holds. */
+int64_t b2rl_replay_device_bytes(const b2rl_replay *h);
+
+/* Copy `n` parts into the ring.  `src` is host (src_on_device = 0; staged
+ * through pinned memory, asynchronous) or device memory, n * part_bytes
+ * contiguous bytes.  The ring slots assigned (sequential modulo
+ * part_capacity) are written to slots_out_host[n].  Replaces the implicit
+ * "keep a reference to the frame ndarray" of the reference. */
+int b2rl_replay_put_parts(b2rl_replay *h, const void *src, int src_on_device,
+                          int64_t n, int32_t *slots_out_host, void *stream);
+
+/* A batch of assembled experiences (structure of arrays, n entries). */
+typedef struct {
+    const int32_t *state_parts; /* [n][stack] part slots of exp[0].state      */
+    const int32_t *next_parts;  /* [n][stack] part slots of exp[-1].next_state*/
+    const void *action;         /* [n][action_bytes]                          */
+    const double *rewards;      /* [n][n_step], entries >= len are ignored    */
+    const uint8_t *len;         /* [n] transitions in the experience, 1..n_step */
+    const uint8_t *terminal;    /* [n] any(is_state_terminal)                 */
+    const double *priority;     /* [n] or NULL = current max_priority
+                                   (collections/prioritized.py:42-44)         */
+} b2rl_experiences;
+
+/* Append n experiences in order, evicting the oldest when full.  Replaces
+ * PrioritizedBuffer.append / popleft (collections/prioritized.py:39-54) and
+ * RandomAccessQueue.append (random_access_queue.py:80-83).  Arrays are host
+ * memory (on_device = 0) or device memory.  n <= capacity. */
+int b2rl_replay_append(b2rl_replay *h, const b2rl_experiences *e, int64_t n,
+                       int on_device, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Prioritized sampling.
+ * ---------------------------------------------------------------------- */
+typedef enum {
+    /* Bit-exact restatement of SumTreeQueue.prioritized_sample(remove=True)
+     * (collections/prioritized.py:294-312): n sequential draws without
+     * replacement, draw k uses pos = u[k] * root_k. */
+    B2RL_SAMPLE_EXACT = 0,
+    /* All n descents run concurrently on the frozen tree (sampling WITH
+     * replacement, pos = u[k] * root_0).  Same marginal distribution for the
+     * first draw; not index-identical to the reference. */
+    B2RL_SAMPLE_PARALLEL = 1
+} b2rl_sample_mode;
+
+/* Draw n leaves.  u_host[n]: uniforms in [0,1) drawn by the caller in the
+ * reference's order (numpy legacy RandomState.random_sample; see
+ * np.random.uniform(0.0, root) at collections/prioritized.py:302).
+ * Outputs (device, may be NULL): index_dev[n] logical indices (0 = oldest),
+ * priority_dev[n] the priorities found (fp64).  The sampled leaves are
+ * zeroed in the sum tree (EXACT mode) until b2rl_per_update_*; the handle
+ * remembers the sampled slots.  Fails with B2RL_ERR_PROTOCOL if a previous
+ * sample has not been answered (collections/prioritized.py:98). */
+int b2rl_per_sample(b2rl_replay *h, const double *u_host, int32_t n, int mode,
+                    int64_t *index_dev, double *priority_dev, void *stream);
+
+typedef enum {
+    B2RL_NORM_NONE = 0,  /* w = (len * prob) ** -beta                         */
+    B2RL_NORM_BATCH = 1, /* w = (prob / min(prob in batch)) ** -beta          */
+    B2RL_NORM_MEMORY = 2 /* w = (prob / (min_tree_root / total)) ** -beta     */
+} b2rl_weight_norm;
+
+/* Importance-sampling weights of the last sample; replaces
+ * PriorityWeightError.weights_from_probabilities
+ * (replay_buffers/prioritized.py:57-66) and the probability computation of
+ * collections/prioritized.py:59-60,79-82.  weight_dev[n] f32 (may be NULL),
+ * prob_dev[n] fp64 (may be NULL). */
+int b2rl_per_weights(b2rl_replay *h, double beta, int norm, float *weight_dev,
+                     double *prob_dev, void *stream);
+
+/* Answer the last sample with new priorities (fp64, > 0; host or device).
+ * Replaces PrioritizedBuffer.set_last_priority
+ * (collections/prioritized.py:107-116): leaves of both trees are rewritten,
+ * max_priority is raised. */
+int b2rl_per_update_priorities(b2rl_replay *h, const double *priority,
+                               int on_device, int32_t n, void *stream);
+
+/* Same, from TD errors on the device (err_is_f64: 0 = float, 1 = double):
+ * priority = (clip(err, error_min, error_max) + eps) ** alpha, replacing
+ * priority_from_errors (replay_buffers/prioritized.py:47-55).  Set
+ * error_min > error_max to disable clipping.  alpha == 0.5 uses sqrt. */
+int b2rl_per_update_errors(b2rl_replay *h, const void *err_dev, int err_is_f64,
+                           int32_t n, double alpha, double eps,
+                           double error_min, double error_max, void *stream);
+
+/* Copy scalar state to the host (synchronises `stream`): total priority,
+ * min-tree root, max_priority, device-side napp / npop. */
+typedef struct {
+    double total;
+    double min;
+    double max_priority;
+    int64_t napp;
+    int64_t npop;
+} b2rl_per_info;
+int b2rl_per_get_info(b2rl_replay *h, b2rl_per_info *out_host, void *stream);
+
+/* Read leaves [first, first+n) of the sum tree by logical index into
+ * out_host (synchronises). Test / checkpoint helper. */
+int b2rl_per_read_priorities(b2rl_replay *h, int64_t first, int64_t n,
+                             double *out_host, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Minibatch gather; replaces batch_experiences (pfrl/replay_buffer.py:
+ * 157-212) + batch_states (pfrl/utils/batch_states.py:18-36) + the H2D copy.
+ * ---------------------------------------------------------------------- */
+typedef enum {
+    B2RL_OBS_RAW = 0,       /* copy part bytes unchanged                      */
+    B2RL_OBS_U8_TO_F32 = 1  /* out = float(u8) * obs_scale  (phi = x/255)     */
+} b2rl_obs_mode;
+
+typedef struct {
+    void *state;      /* [n][stack*part_bytes] bytes, or f32 [n][stack*part_bytes] */
+    void *next_state; /* same layout                                          */
+    void *action;     /* [n][action_bytes]                                    */
+    float *reward;    /* [n] sum_i gamma^i r_i, fp64 compensated sum -> f32   */
+    float *terminal;  /* [n] 1.0 if any transition terminal                   */
+    float *discount;  /* [n] gamma ** len                                     */
+} b2rl_batch_out;
+
+/* index_dev: n logical indices on the device, or NULL to gather the
+ * experiences drawn by the last b2rl_per_sample.  gamma_pow_host[n_step+1]
+ * holds gamma**i computed by the caller (CPython float pow, so the bits match
+ * the reference's `gamma**i`).  Any output pointer may be NULL. */
+int b2rl_replay_gather(b2rl_replay *h, const int64_t *index_dev, int32_t n,
+                       const double *gamma_pow_host, int obs_mode,
+                       float obs_scale, const b2rl_batch_out *out,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2RL_H */

@@ -1,0 +1,500 @@
+// sampler.cu -- prioritized sampling, IS weights and priority write-back on
+// the dense fp64 heaps.
+//
+// Replaces (reference, pure Python):
+//   pfrl/collections/prioritized.py:56-116   _sample_indices_and_probabilities,
+//                                            sample, set_last_priority
+//   pfrl/collections/prioritized.py:245-258  _find
+//   pfrl/collections/prioritized.py:294-312  SumTreeQueue.prioritized_sample
+//   pfrl/replay_buffers/prioritized.py:47-66 priority_from_errors,
+//                                            weights_from_probabilities
+//
+// EXACT mode reproduces the reference's sampled indices bit for bit: the
+// draws are a dependent chain (draw k sees the root after the k-1 earlier
+// hits were zeroed and their paths re-reduced), so one warp walks them in
+// order.  What makes it fast is where the chain's operands live: the top
+// TOP_LEVELS levels of the sum tree are staged in shared memory for the
+// whole launch, and the remaining levels under the chosen top node are
+// fetched by the 32 lanes in ONE round trip (each level's slice of a subtree
+// is contiguous in the heap), so a draw costs one global latency, not one per
+// level.
+#include <math.h>
+
+#include "b2rl_internal.cuh"
+
+#define TRY(x)                                                                 \
+    do {                                                                       \
+        int rc__ = (x);                                                        \
+        if (rc__ != B2RL_OK) return rc__;                                      \
+    } while (0)
+
+static constexpr int TOP_LEVELS = 14; // heap levels 0..13 -> 16383 nodes = 128 KB
+
+struct SampleArgs {
+    double *sum;
+    const double *mn;
+    B2rlDevState *st;
+    const double *u;
+    int n;
+    int levels;      // leaves are at heap level `levels`
+    long long nslots;
+    int T;           // levels held in shared memory (nodes [1, 2^T))
+    int D;           // levels below the shared part (0: leaves are in shared)
+    int32_t *slots_out;
+    double *prio_out;
+    long long *index_out; // optional
+    double *prio_user;    // optional
+};
+
+extern __shared__ double smem_d[];
+
+__global__ void __launch_bounds__(256, 1) k_sample_exact(SampleArgs a)
+{
+    double *top = smem_d;
+    double *sub = smem_d + (1 << a.T);
+    const int topn = 1 << a.T;
+    const int tid = threadIdx.x;
+    for (int i = 1 + tid; i < topn; i += blockDim.x) top[i] = a.sum[i];
+    __syncthreads();
+
+    if (tid < 32) {
+        const int lane = tid;
+        const long long mask = a.nslots - 1;
+        const long long npop = a.st->npop;
+        // The reference's root visits its OLDER half first
+        // (collections/prioritized.py:255-258 with the bounds of :229-241).
+        const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+        if (lane == 0) {
+            a.st->last_total = top[1]; // priority_sums.sum(), :58
+            a.st->last_min = a.mn[1];  // priority_mins.min(), :59
+            a.st->last_n = a.n;
+        }
+        double unext = a.n > 0 ? a.u[0] : 0.0;
+        for (int k = 0; k < a.n; k++) {
+            const double uk = unext;
+            if (k + 1 < a.n) unext = a.u[k + 1];
+            // np.random.uniform(0.0, root) = 0.0 + (root - 0.0) * u, :302
+            double pos = __dmul_rn(top[1], uk);
+            // _find, :245-258
+            int node = older;
+            {
+                const double left = top[older];
+                if (!(pos < left)) {
+                    pos = __dsub_rn(pos, left);
+                    node = older ^ 1;
+                }
+            }
+            for (int lv = 1; lv < a.T - 1; lv++) {
+                const double left = top[2 * node];
+                if (pos < left) {
+                    node = 2 * node;
+                } else {
+                    pos = __dsub_rn(pos, left);
+                    node = 2 * node + 1;
+                }
+            }
+            long long leafnode;
+            double prio;
+            if (a.D > 0) {
+                // one round trip: all D levels under `node`
+                for (int j = 1; j <= a.D; j++) {
+                    const int cnt = 1 << j;
+                    const double *src = a.sum + ((long long)node << j);
+                    for (int i = lane; i < cnt; i += 32) sub[cnt + i] = src[i];
+                }
+                __syncwarp();
+                int rel = 1;
+                for (int j = 0; j < a.D; j++) {
+                    const double left = sub[2 * rel];
+                    if (pos < left) {
+                        rel = 2 * rel;
+                    } else {
+                        pos = __dsub_rn(pos, left);
+                        rel = 2 * rel + 1;
+                    }
+                }
+                leafnode = ((long long)node << a.D) + (rel - (1 << a.D));
+                prio = sub[rel];
+                // _write(ix, 0.0): zero the leaf, re-reduce the path, :303
+                sub[rel] = 0.0;
+                if (lane == 0) a.sum[leafnode] = 0.0;
+                int dj = a.D - 1;
+                for (int p = rel >> 1; p >= 2; p >>= 1, dj--) {
+                    const double v = __dadd_rn(sub[2 * p], sub[2 * p + 1]);
+                    sub[p] = v;
+                    if (lane == 0) a.sum[((long long)node << dj) + (p - (1 << dj))] = v;
+                }
+                top[node] = __dadd_rn(sub[2], sub[3]);
+            } else {
+                leafnode = node;
+                prio = top[node];
+                top[node] = 0.0;
+            }
+            for (int p = node >> 1; p >= 1; p >>= 1)
+                top[p] = __dadd_rn(top[2 * p], top[2 * p + 1]);
+            if (lane == 0) {
+                const long long slot = leafnode - a.nslots;
+                a.slots_out[k] = (int32_t)slot;
+                a.prio_out[k] = prio;
+                if (a.index_out) a.index_out[k] = (slot - npop) & mask;
+                if (a.prio_user) a.prio_user[k] = prio;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // publish the shared-memory levels (zeroed state) back to HBM
+    for (int i = 1 + tid; i < topn; i += blockDim.x) a.sum[i] = top[i];
+}
+
+// PARALLEL mode: every draw descends the frozen tree on its own thread.
+__global__ void k_sample_parallel(SampleArgs a)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long mask = a.nslots - 1;
+    const long long npop = a.st->npop;
+    const double root = a.sum[1];
+    if (k == 0) {
+        a.st->last_total = root;
+        a.st->last_min = a.mn[1];
+        a.st->last_n = a.n;
+    }
+    if (k >= a.n) return;
+    const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+    double pos = __dmul_rn(root, a.u[k]);
+    long long node = older;
+    {
+        const double left = a.sum[older];
+        if (!(pos < left)) {
+            pos = __dsub_rn(pos, left);
+            node = older ^ 1;
+        }
+    }
+    for (int lv = 1; lv < a.levels; lv++) {
+        const double2 c = *reinterpret_cast<const double2 *>(a.sum + 2 * node);
+        if (pos < c.x) {
+            node = 2 * node;
+        } else {
+            pos = __dsub_rn(pos, c.x);
+            node = 2 * node + 1;
+        }
+    }
+    const double prio = a.sum[node];
+    const long long slot = node - a.nslots;
+    a.slots_out[k] = (int32_t)slot;
+    a.prio_out[k] = prio;
+    if (a.index_out) a.index_out[k] = (slot - npop) & mask;
+    if (a.prio_user) a.prio_user[k] = prio;
+}
+
+extern "C" int b2rl_per_sample(b2rl_replay *h, const double *u_host, int32_t n, int mode,
+                               int64_t *index_dev, double *priority_dev, void *stream)
+{
+    B2RL_REQUIRE(h && u_host, B2RL_ERR_INVALID, "null argument");
+    B2RL_REQUIRE(h->cfg.prioritized, B2RL_ERR_INVALID, "buffer has no priority trees");
+    B2RL_REQUIRE(n > 0 && n <= h->cfg.max_batch, B2RL_ERR_RANGE, "sample: n=%d out of 1..max_batch=%d",
+                 n, h->cfg.max_batch);
+    B2RL_REQUIRE(n <= h->napp - h->npop, B2RL_ERR_RANGE,
+                 "sample: n=%d exceeds the %lld stored experiences", n,
+                 (long long)(h->napp - h->npop));
+    B2RL_REQUIRE(!h->wait_priority, B2RL_ERR_PROTOCOL,
+                 "sample() called again before the previous sample's priorities were set "
+                 "(collections/prioritized.py:98)");
+    B2RL_REQUIRE(mode == B2RL_SAMPLE_EXACT || mode == B2RL_SAMPLE_PARALLEL, B2RL_ERR_INVALID,
+                 "unknown sample mode %d", mode);
+    cudaStream_t s = (cudaStream_t)stream;
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    for (int i = 0; i < n; i++)
+        B2RL_REQUIRE(u_host[i] >= 0.0 && u_host[i] < 1.0, B2RL_ERR_INVALID,
+                     "sample: u[%d]=%g not in [0,1)", i, u_host[i]);
+    TRY(b2rl_stage_acquire(h, (size_t)n * 8));
+    memcpy(h->pin, u_host, (size_t)n * 8);
+    B2RL_CUDA(cudaMemcpyAsync(h->u_dev, h->pin, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    TRY(b2rl_stage_release(h, s));
+
+    SampleArgs a;
+    a.sum = h->sum;
+    a.mn = h->mn;
+    a.st = h->st;
+    a.u = h->u_dev;
+    a.n = n;
+    a.levels = h->levels;
+    a.nslots = h->nslots;
+    a.T = h->levels + 1 < TOP_LEVELS ? h->levels + 1 : TOP_LEVELS;
+    a.D = h->levels - (a.T - 1);
+    a.slots_out = h->last_slots;
+    a.prio_out = h->last_prio;
+    a.index_out = (long long *)index_dev;
+    a.prio_user = priority_dev;
+    if (mode == B2RL_SAMPLE_EXACT) {
+        size_t smem = sizeof(double) * ((size_t(1) << a.T) + (size_t(2) << a.D));
+        static bool attr_set = false;
+        if (!attr_set) {
+            B2RL_CUDA(cudaFuncSetAttribute(k_sample_exact,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           200 * 1024));
+            attr_set = true;
+        }
+        k_sample_exact<<<1, 256, smem, s>>>(a);
+    } else {
+        k_sample_parallel<<<(n + 127) / 128, 128, 0, s>>>(a);
+    }
+    B2RL_CUDA(cudaGetLastError());
+    h->wait_priority = true;
+    h->last_n = n;
+    h->last_mode = mode;
+    return B2RL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// importance-sampling weights
+// ---------------------------------------------------------------------------
+struct WeightArgs {
+    const B2rlDevState *st;
+    const double *prio;
+    int n;
+    double beta;
+    int norm;
+    float *weight;
+    double *prob;
+};
+
+__global__ void __launch_bounds__(1024) k_weights(WeightArgs a)
+{
+    __shared__ double red[32];
+    __shared__ double s_min;
+    const double total = a.st->last_total;
+    double denom;
+    if (a.norm == B2RL_NORM_BATCH) {
+        // np.min(probabilities), replay_buffers/prioritized.py:60
+        double m = INFINITY;
+        for (int k = threadIdx.x; k < a.n; k += blockDim.x) m = fmin(m, a.prio[k] / total);
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : INFINITY;
+            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (threadIdx.x == 0) s_min = m;
+        }
+        __syncthreads();
+        denom = s_min;
+    } else if (a.norm == B2RL_NORM_MEMORY) {
+        denom = a.st->last_min / total; // collections/prioritized.py:60
+    } else {
+        denom = 0.0;
+    }
+    const double len = (double)(a.st->napp - a.st->npop);
+    for (int k = threadIdx.x; k < a.n; k += blockDim.x) {
+        const double p = a.prio[k] / total; // :79-82 with uniform_ratio == 0
+        if (a.prob) a.prob[k] = p;
+        if (a.weight) {
+            const double base = (a.norm == B2RL_NORM_NONE) ? len * p : p / denom;
+            a.weight[k] = (float)pow(base, -a.beta); // :62 / :64
+        }
+    }
+}
+
+extern "C" int b2rl_per_weights(b2rl_replay *h, double beta, int norm, float *weight_dev,
+                                double *prob_dev, void *stream)
+{
+    B2RL_REQUIRE(h, B2RL_ERR_INVALID, "null handle");
+    B2RL_REQUIRE(h->wait_priority && h->last_n > 0, B2RL_ERR_PROTOCOL,
+                 "weights requested without a pending sample");
+    B2RL_REQUIRE(norm >= 0 && norm <= 2, B2RL_ERR_INVALID, "unknown normalisation %d", norm);
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    WeightArgs a{h->st, h->last_prio, h->last_n, beta, norm, weight_dev, prob_dev};
+    k_weights<<<1, 1024, 0, (cudaStream_t)stream>>>(a);
+    B2RL_CUDA(cudaGetLastError());
+    return B2RL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// priority write-back
+// ---------------------------------------------------------------------------
+struct UpdateArgs {
+    double *sum, *mn;
+    B2rlDevState *st;
+    const int32_t *slots;
+    double *new_prio;       // [n] priorities (input, or scratch for the error form)
+    const void *err;        // optional TD errors
+    int err_is_f64;
+    double alpha, eps, emin, emax;
+    int32_t *winner;
+    int n, levels;
+    long long nslots;
+};
+
+__global__ void __launch_bounds__(1024) k_update(UpdateArgs a)
+{
+    __shared__ double red[32];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (a.err) {
+        // priority_from_errors, replay_buffers/prioritized.py:47-55
+        for (int k = tid; k < a.n; k += nt) {
+            double d = a.err_is_f64 ? ((const double *)a.err)[k] : (double)((const float *)a.err)[k];
+            if (a.emin <= a.emax) d = fmin(fmax(d, a.emin), a.emax);
+            d += a.eps;
+            a.new_prio[k] = (a.alpha == 0.5) ? sqrt(d) : pow(d, a.alpha);
+        }
+    }
+    // duplicates: the reference writes in order, so the LAST occurrence wins
+    for (int k = tid; k < a.n; k += nt) atomicMax(&a.winner[a.slots[k]], k);
+    __syncthreads();
+    double mx = 0.0;
+    for (int k = tid; k < a.n; k += nt) {
+        const double p = a.new_prio[k];
+        mx = fmax(mx, p); // max_priority sees every value, :114
+        const long long leaf = a.nslots + a.slots[k];
+        if (a.winner[a.slots[k]] == k) {
+            a.sum[leaf] = p;
+            a.mn[leaf] = p;
+        }
+    }
+    __syncthreads();
+    for (int lv = a.levels - 1; lv >= 0; lv--) {
+        const long long width = 1ll << lv;
+        if (width <= a.n) {
+            for (long long node = width + tid; node < 2 * width; node += nt) {
+                a.sum[node] = a.sum[2 * node] + a.sum[2 * node + 1];
+                a.mn[node] = fmin(a.mn[2 * node], a.mn[2 * node + 1]);
+            }
+        } else {
+            const int sh = a.levels - lv;
+            for (int k = tid; k < a.n; k += nt) {
+                const long long node = (a.nslots + a.slots[k]) >> sh;
+                a.sum[node] = a.sum[2 * node] + a.sum[2 * node + 1];
+                a.mn[node] = fmin(a.mn[2 * node], a.mn[2 * node + 1]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < a.n; k += nt) a.winner[a.slots[k]] = -1;
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid < 32) {
+        mx = tid < (nt >> 5) ? red[tid] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (tid == 0) {
+            if (mx > a.st->max_priority) a.st->max_priority = mx;
+            a.st->last_n = 0;
+        }
+    }
+}
+
+static int launch_update(b2rl_replay *h, int32_t n, const void *err, int err_is_f64, double alpha,
+                         double eps, double emin, double emax, cudaStream_t s)
+{
+    UpdateArgs a;
+    a.sum = h->sum;
+    a.mn = h->mn;
+    a.st = h->st;
+    a.slots = h->last_slots;
+    a.new_prio = h->new_prio;
+    a.err = err;
+    a.err_is_f64 = err_is_f64;
+    a.alpha = alpha;
+    a.eps = eps;
+    a.emin = emin;
+    a.emax = emax;
+    a.winner = h->winner;
+    a.n = n;
+    a.levels = h->levels;
+    a.nslots = h->nslots;
+    k_update<<<1, 1024, 0, s>>>(a);
+    B2RL_CUDA(cudaGetLastError());
+    h->wait_priority = false;
+    h->last_n = 0;
+    return B2RL_OK;
+}
+
+static int check_update(b2rl_replay *h, int32_t n)
+{
+    B2RL_REQUIRE(h, B2RL_ERR_INVALID, "null handle");
+    B2RL_REQUIRE(h->wait_priority, B2RL_ERR_PROTOCOL,
+                 "priorities set without a pending sample (collections/prioritized.py:108)");
+    B2RL_REQUIRE(n == h->last_n, B2RL_ERR_RANGE,
+                 "got %d priorities for a sample of %d (collections/prioritized.py:110)", n,
+                 h->last_n);
+    return B2RL_OK;
+}
+
+extern "C" int b2rl_per_update_priorities(b2rl_replay *h, const double *priority, int on_device,
+                                          int32_t n, void *stream)
+{
+    TRY(check_update(h, n));
+    B2RL_REQUIRE(priority, B2RL_ERR_INVALID, "null priorities");
+    cudaStream_t s = (cudaStream_t)stream;
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    if (on_device) {
+        B2RL_CUDA(cudaMemcpyAsync(h->new_prio, priority, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+    } else {
+        for (int i = 0; i < n; i++)
+            B2RL_REQUIRE(priority[i] > 0.0, B2RL_ERR_INVALID,
+                         "priority[%d]=%g must be > 0 (collections/prioritized.py:109)", i,
+                         priority[i]);
+        TRY(b2rl_stage_acquire(h, (size_t)n * 8));
+        memcpy(h->pin, priority, (size_t)n * 8);
+        B2RL_CUDA(cudaMemcpyAsync(h->new_prio, h->pin, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        TRY(b2rl_stage_release(h, s));
+    }
+    return launch_update(h, n, nullptr, 0, 0, 0, 0, 0, s);
+}
+
+extern "C" int b2rl_per_update_errors(b2rl_replay *h, const void *err_dev, int err_is_f64,
+                                      int32_t n, double alpha, double eps, double error_min,
+                                      double error_max, void *stream)
+{
+    TRY(check_update(h, n));
+    B2RL_REQUIRE(err_dev, B2RL_ERR_INVALID, "null errors");
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    return launch_update(h, n, err_dev, err_is_f64, alpha, eps, error_min, error_max,
+                         (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------
+extern "C" int b2rl_per_get_info(b2rl_replay *h, b2rl_per_info *out, void *stream)
+{
+    B2RL_REQUIRE(h && out, B2RL_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    B2rlDevState st;
+    B2RL_CUDA(cudaMemcpyAsync(&st, h->st, sizeof(st), cudaMemcpyDeviceToHost, s));
+    double roots[2] = {0.0, INFINITY};
+    if (h->cfg.prioritized) {
+        B2RL_CUDA(cudaMemcpyAsync(&roots[0], h->sum + 1, 8, cudaMemcpyDeviceToHost, s));
+        B2RL_CUDA(cudaMemcpyAsync(&roots[1], h->mn + 1, 8, cudaMemcpyDeviceToHost, s));
+    }
+    B2RL_CUDA(cudaStreamSynchronize(s));
+    out->total = roots[0];
+    out->min = roots[1];
+    out->max_priority = st.max_priority;
+    out->napp = st.napp;
+    out->npop = st.npop;
+    return B2RL_OK;
+}
+
+extern "C" int b2rl_per_read_priorities(b2rl_replay *h, int64_t first, int64_t n, double *out,
+                                        void *stream)
+{
+    B2RL_REQUIRE(h && out, B2RL_ERR_INVALID, "null argument");
+    B2RL_REQUIRE(h->cfg.prioritized, B2RL_ERR_INVALID, "buffer has no priority trees");
+    B2RL_REQUIRE(first >= 0 && n >= 0 && first + n <= h->napp - h->npop, B2RL_ERR_RANGE,
+                 "read_priorities: range out of bounds");
+    cudaStream_t s = (cudaStream_t)stream;
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    const int64_t mask = h->nslots - 1;
+    int64_t done = 0;
+    while (done < n) {
+        int64_t slot = (h->npop + first + done) & mask;
+        int64_t run = n - done < h->nslots - slot ? n - done : h->nslots - slot;
+        B2RL_CUDA(cudaMemcpyAsync(out + done, h->sum + h->nslots + slot, (size_t)run * 8,
+                                  cudaMemcpyDeviceToHost, s));
+        done += run;
+    }
+    B2RL_CUDA(cudaStreamSynchronize(s));
+    return B2RL_OK;
+}
