@@ -203,6 +203,8 @@ typedef struct {
     float *reward;    /* [n] sum_i gamma^i r_i, fp64 compensated sum -> f32   */
     float *terminal;  /* [n] 1.0 if any transition terminal                   */
     float *discount;  /* [n] gamma ** len                                     */
+    double *step_rewards; /* [n][n_step] raw per-step rewards (entries >= len are 0) */
+    uint8_t *len;     /* [n] transitions per experience                       */
 } b2rl_batch_out;
 
 /* index_dev: n logical indices on the device, or NULL to gather the

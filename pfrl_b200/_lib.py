@@ -88,6 +88,8 @@ class BatchOut(ctypes.Structure):
         ("reward", ctypes.c_void_p),
         ("terminal", ctypes.c_void_p),
         ("discount", ctypes.c_void_p),
+        ("step_rewards", ctypes.c_void_p),
+        ("len", ctypes.c_void_p),
     ]
 
 

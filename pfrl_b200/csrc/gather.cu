@@ -31,6 +31,8 @@ struct GatherArgs {
     float obs_scale;
     uint8_t *o_state, *o_next, *o_action;
     float *o_reward, *o_terminal, *o_discount;
+    double *o_step_rewards;
+    uint8_t *o_len;
 };
 
 __device__ __forceinline__ long long gather_slot(const GatherArgs &a, int k)
@@ -100,6 +102,10 @@ __global__ void __launch_bounds__(256) k_gather(GatherArgs a)
     }
     if (a.o_terminal) a.o_terminal[k] = a.terminal[slot] ? 1.0f : 0.0f;
     if (a.o_discount) a.o_discount[k] = (float)a.gamma_pow[len]; // gamma ** len(elem), :203
+    if (a.o_len) a.o_len[k] = (uint8_t)len;
+    if (a.o_step_rewards)
+        for (int i = 0; i < a.n_step; i++)
+            a.o_step_rewards[(size_t)k * a.n_step + i] = i < len ? a.rewards[slot * a.n_step + i] : 0.0;
     if (a.o_action) {
         const uint8_t *src = a.action + slot * a.action_bytes;
         uint8_t *dst = a.o_action + (size_t)k * a.action_bytes;
@@ -149,6 +155,8 @@ extern "C" int b2rl_replay_gather(b2rl_replay *h, const int64_t *index_dev, int3
     a.o_reward = out->reward;
     a.o_terminal = out->terminal;
     a.o_discount = out->discount;
+    a.o_step_rewards = out->step_rewards;
+    a.o_len = out->len;
     const int items = n * 2 * c.stack;
     const int tail = (n + 255) / 256;
     k_gather<<<items + tail, 256, 0, s>>>(a);

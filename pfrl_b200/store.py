@@ -173,7 +173,7 @@ class DeviceReplayStore:
     # -- gather --------------------------------------------------------------
     def gather(self, n, gamma_pow, index=None, obs_mode=OBS_RAW, obs_scale=1.0,
                obs_dtype=None, obs_shape=None, action_dtype=torch.int64,
-               action_shape=(), want_obs=True):
+               action_shape=(), want_obs=True, want_steps=False):
         """Assemble a minibatch.  index: CUDA int64 tensor of logical indices,
         or None for the experiences of the pending prioritized sample."""
         gp = np.ascontiguousarray(gamma_pow, dtype=np.float64)
@@ -194,11 +194,16 @@ class DeviceReplayStore:
         out["reward"] = torch.empty(n, dtype=torch.float32, device=dev)
         out["is_state_terminal"] = torch.empty(n, dtype=torch.float32, device=dev)
         out["discount"] = torch.empty(n, dtype=torch.float32, device=dev)
+        if want_steps:
+            out["step_rewards"] = torch.empty((n, self.n_step), dtype=torch.float64, device=dev)
+            out["len"] = torch.empty(n, dtype=torch.uint8, device=dev)
         bo = _lib.BatchOut(
             state=out["state"].data_ptr() if want_obs else None,
             next_state=out["next_state"].data_ptr() if want_obs else None,
             action=out["action"].data_ptr(), reward=out["reward"].data_ptr(),
             terminal=out["is_state_terminal"].data_ptr(), discount=out["discount"].data_ptr(),
+            step_rewards=out["step_rewards"].data_ptr() if want_steps else None,
+            len=out["len"].data_ptr() if want_steps else None,
         )
         _lib.check(self.L.b2rl_replay_gather(
             self.h, ctypes.c_void_p(index.data_ptr()) if index is not None else None, n,

@@ -1,0 +1,38 @@
+"""Parameter copies between networks (pfrl/utils/copy_param.py)."""
+import torch
+
+
+def copy_param(target_link, source_link):
+    """Hard copy of every state_dict entry (copy_param.py:4-6)."""
+    target_link.load_state_dict(source_link.state_dict())
+
+
+@torch.no_grad()
+def soft_copy_param(target_link, source_link, tau):
+    """Polyak averaging ``target = (1 - tau) * target + tau * source`` over
+    floating state_dict entries; integer buffers are copied
+    (copy_param.py:9-22).  One fused multi-tensor launch on CUDA."""
+    tgt = target_link.state_dict()
+    src = source_link.state_dict()
+    f_t, f_s = [], []
+    for k, tv in tgt.items():
+        sv = src[k]
+        if tv.dtype in (torch.float16, torch.bfloat16, torch.float32, torch.float64):
+            assert tv.shape == sv.shape
+            f_t.append(tv)
+            f_s.append(sv)
+        else:
+            tv.copy_(sv)
+    if f_t:
+        torch._foreach_mul_(f_t, 1.0 - tau)
+        torch._foreach_add_(f_t, f_s, alpha=tau)
+
+
+def synchronize_parameters(src, dst, method, tau=None):
+    """copy_param.py:37-41"""
+    if method == "hard":
+        copy_param(dst, src)
+    elif method == "soft":
+        soft_copy_param(dst, src, tau)
+    else:
+        raise ValueError("unknown target update method: %r" % (method,))
