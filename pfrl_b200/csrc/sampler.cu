@@ -147,6 +147,238 @@ __global__ void __launch_bounds__(256, 1) k_sample_exact(SampleArgs a)
     for (int i = 1 + tid; i < topn; i += blockDim.x) a.sum[i] = top[i];
 }
 
+// ---------------------------------------------------------------------------
+// Latency-engineered EXACT sampler for deep trees (levels >= 13).
+//
+// The draws are a dependent chain, so throughput = 1 / (latency of one draw).
+// Per draw the critical path is: descent (compare / subtract per level) ->
+// leaf -> bottom-up re-reduction (one add per level) -> new root.  This
+// version shortens it three ways:
+//   * speculative descent: the 32 lanes evaluate all 2^R continuations of R
+//     levels at once (lane i follows the path whose turn bits are i).  The R
+//     `left` operands of every lane depend only on (node, lane), so they are
+//     fetched together; the per-lane chain is R predicated subtractions with
+//     the comparisons off the critical path; one ballot picks the lane whose
+//     comparisons are all consistent.  5 levels cost ~1 shared-memory latency
+//     + 5 DADD instead of 5 x (LDS + compare + select).
+//   * the D levels below the shared-memory top are fetched as double2 child
+//     pairs, all loads of a lane in flight together: one HBM/L2 round trip.
+//   * the re-reduction loads all 13 + D siblings first (independent), then
+//     runs the 13 + D dependent adds out of registers; stores are fire and
+//     forget.
+// The arithmetic (order of every compare, subtract and add) is exactly that
+// of the reference, so indices stay bit-identical.
+// ---------------------------------------------------------------------------
+// L2 residency: the sum tree (32 MB at 1M capacity) is re-read by every
+// draw while the gather streams ~140 MB per minibatch through the same L2.
+// Tree accesses carry an evict_last policy (the gather's stores are .cs /
+// evict-first), so the descent's one global round trip per draw tends to be an
+// L2 hit instead of an HBM access.
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ double2 ld_tree_pair(const double2 *ptr, uint64_t pol)
+{
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ void st_tree(double *ptr, double v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol)
+                 : "memory");
+}
+
+template <int R>
+__device__ __forceinline__ void spec_round(const double *val, int &node, double &pos, int lane)
+{
+    static_assert(R >= 1 && R <= 5, "one round covers at most 5 levels");
+    const int li = lane & ((1 << R) - 1);
+    double left[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int nj = (node << j) + (li >> (R - j));
+        left[j] = val[2 * nj];
+    }
+    double x = pos;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const bool right = (li >> (R - 1 - j)) & 1;
+        const bool lt = x < left[j];
+        ok = ok && (lt != right);
+        if (right) x = __dsub_rn(x, left[j]);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if constexpr (R < 5) m &= (1u << (1 << R)) - 1u;
+    const int win = __ffs(m) - 1;
+    pos = __shfl_sync(0xffffffffu, x, win);
+    node = (node << R) + win;
+}
+
+template <int L>
+__device__ __forceinline__ void spec_descend(const double *val, int &node, double &pos, int lane)
+{
+    if constexpr (L > 0) {
+        constexpr int R = L >= 5 ? 5 : L;
+        spec_round<R>(val, node, pos, lane);
+        spec_descend<L - R>(val, node, pos, lane);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, 1) k_sample_exact_deep(SampleArgs a)
+{
+    constexpr int T = TOP_LEVELS; // shared memory holds heap levels 0..T-1
+    constexpr int TOPN = 1 << T;
+    constexpr int PAIRS = (1 << D) - 1;       // child pairs below the chosen top node
+    constexpr int NIT = (PAIRS + 31) / 32;
+    double *top = smem_d;
+    double *sub = smem_d + TOPN;
+    const int tid = threadIdx.x;
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(a.sum);
+        double2 *dst = reinterpret_cast<double2 *>(top);
+        for (int i = tid; i < TOPN / 2; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    if (tid < 32) {
+        const int lane = tid;
+        const long long mask = a.nslots - 1;
+        const long long npop = a.st->npop;
+        const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+        const uint64_t pol = policy_evict_last();
+        const double2 *sum2 = reinterpret_cast<const double2 *>(a.sum);
+        if (lane == 0) {
+            a.st->last_total = top[1];
+            a.st->last_min = a.mn[1];
+            a.st->last_n = a.n;
+        }
+        double unext = a.u[0];
+        for (int k = 0; k < a.n; k++) {
+            const double uk = unext;
+            if (k + 1 < a.n) unext = a.u[k + 1];
+            double pos = __dmul_rn(top[1], uk);
+            int node = older;
+            {
+                const double left = top[older];
+                if (!(pos < left)) {
+                    pos = __dsub_rn(pos, left);
+                    node = older ^ 1;
+                }
+            }
+            spec_descend<T - 2>(top, node, pos, lane); // level 1 -> T-1
+            // ---- one round trip for the D levels under `node` ----------------
+            // lane-constant (q, depth, offset) per unrolled load; q = 0 is
+            // clamped to 1 and q > PAIRS cannot happen (PAIRS + 1 = 2^D)
+            double2 tmp[NIT];
+            const unsigned unode = (unsigned)node;
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                int q = lane + 32 * it;
+                q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                const int dq = 31 - __clz(q);
+                const unsigned g = (unode << dq) + (unsigned)(q - (1 << dq));
+                tmp[it] = ld_tree_pair(sum2 + g, pol);
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                int q = lane + 32 * it;
+                q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                reinterpret_cast<double2 *>(sub)[q] = tmp[it];
+            }
+            __syncwarp();
+            int rel = 1;
+            spec_descend<D>(sub, rel, pos, lane);
+            const unsigned leafnode = (unode << D) + (unsigned)(rel - (1 << D));
+            const double prio = sub[rel];
+            // ---- re-reduce the path: siblings first, then the add chain -------
+            double sib[D + T - 1];
+#pragma unroll
+            for (int j = 0; j < D; j++) sib[j] = sub[(rel >> j) ^ 1];
+#pragma unroll
+            for (int j = 0; j < T - 1; j++) sib[D + j] = top[(node >> j) ^ 1];
+            double v = 0.0;
+            if (lane == 0) st_tree(a.sum + leafnode, 0.0, pol);
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                v = __dadd_rn(v, sib[j]);
+                if (lane == 0) {
+                    if (j + 1 < D) {
+                        const int dp = D - j - 1; // depth of the relative parent
+                        const unsigned p = (unsigned)(rel >> (j + 1));
+                        st_tree(a.sum + ((unode << dp) + (p - (1u << dp))), v, pol);
+                    } else {
+                        top[node] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < T - 1; j++) {
+                v = __dadd_rn(v, sib[D + j]);
+                if (lane == 0) top[node >> (j + 1)] = v;
+            }
+            if (lane == 0) {
+                const long long slot = (long long)leafnode - a.nslots;
+                a.slots_out[k] = (int32_t)slot;
+                a.prio_out[k] = prio;
+                if (a.index_out) a.index_out[k] = (slot - npop) & mask;
+                if (a.prio_user) a.prio_user[k] = prio;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    {
+        double2 *dst = reinterpret_cast<double2 *>(a.sum);
+        const double2 *src = reinterpret_cast<const double2 *>(top);
+        for (int i = tid; i < TOPN / 2; i += blockDim.x)
+            if (i > 0) dst[i] = src[i];
+        if (tid == 0) a.sum[1] = top[1];
+    }
+}
+
+template <int D>
+static cudaError_t launch_deep(const SampleArgs &a, cudaStream_t s)
+{
+    const size_t smem = sizeof(double) * ((size_t(1) << TOP_LEVELS) + (size_t(2) << D));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_sample_exact_deep<D>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_sample_exact_deep<D><<<1, 256, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_exact_deep(const SampleArgs &a, cudaStream_t s)
+{
+    switch (a.D) {
+    case 1: return launch_deep<1>(a, s);
+    case 2: return launch_deep<2>(a, s);
+    case 3: return launch_deep<3>(a, s);
+    case 4: return launch_deep<4>(a, s);
+    case 5: return launch_deep<5>(a, s);
+    case 6: return launch_deep<6>(a, s);
+    case 7: return launch_deep<7>(a, s);
+    case 8: return launch_deep<8>(a, s);
+    case 9: return launch_deep<9>(a, s);
+    case 10: return launch_deep<10>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 // PARALLEL mode: every draw descends the frozen tree on its own thread.
 __global__ void k_sample_parallel(SampleArgs a)
 {
@@ -226,7 +458,9 @@ extern "C" int b2rl_per_sample(b2rl_replay *h, const double *u_host, int32_t n, 
     a.prio_out = h->last_prio;
     a.index_out = (long long *)index_dev;
     a.prio_user = priority_dev;
-    if (mode == B2RL_SAMPLE_EXACT) {
+    if (mode == B2RL_SAMPLE_EXACT && a.D > 0) {
+        B2RL_CUDA(launch_exact_deep(a, s));
+    } else if (mode == B2RL_SAMPLE_EXACT) {
         size_t smem = sizeof(double) * ((size_t(1) << a.T) + (size_t(2) << a.D));
         static bool attr_set = false;
         if (!attr_set) {

@@ -207,6 +207,87 @@ class DeviceNStepBuffer:
 
         persistence.load_buffer(self, filename)
 
+    def append_trajectory(self, frames, actions, rewards, terminals=None, env_id=0):
+        """Bulk-append one environment's pre-recorded trajectory.
+
+        ``frames``: uint8 array / CUDA tensor ``[T + stack, *frame_shape]``;
+        the observation at step t is ``frames[t : t + stack]`` (frame
+        stacking with shared frames, like VectorFrameStack + LazyFrames).
+        ``actions[T]``, ``rewards[T]``, ``terminals[T]`` describe the T
+        transitions.  Produces exactly the experiences the per-transition
+        ``append`` would (n-step windows, shorter tails at terminals; an
+        unfinished tail at the end is NOT emitted), in the same order, but
+        assembles them with vectorised numpy and uploads the frames in one
+        copy.  ``stack`` is taken from the buffer layout if it exists, else
+        must be given by a previous ``append``/``configure``.
+        """
+        if self._pend_exp or self._pend_parts:
+            self._flush()
+        T = len(actions)
+        stack = self._traj_stack
+        assert frames.shape[0] == T + stack
+        if terminals is None:
+            terminals = np.zeros(T, dtype=bool)
+        terminals = np.asarray(terminals, dtype=bool)
+        if self.store is None:
+            class _Probe:  # LazyFrames-like layout probe
+                pass
+            probe = _Probe()
+            probe._frames = [frames[i][None] if frames[i].dim() == 2 else frames[i]
+                             for i in range(stack)] if isinstance(frames, torch.Tensor) else \
+                [np.asarray(frames[i])[None] if np.asarray(frames[i]).ndim == 2 else np.asarray(frames[i])
+                 for i in range(stack)]
+            self._create_store(probe, actions[0])
+        lay = self.layout
+        n_frames = frames.shape[0]
+        assert n_frames <= self._part_capacity
+        # upload the frames: sequential ring slots
+        if isinstance(frames, torch.Tensor):
+            fb = frames.contiguous().view(n_frames, -1)
+            assert fb.shape[1] == lay.part_bytes, "frame bytes must be a multiple of 16"
+            slots = self.store.put_parts(fb)
+        else:
+            fb = np.ascontiguousarray(frames).reshape(n_frames, -1).view(np.uint8)
+            assert fb.shape[1] == lay.part_bytes, "frame bytes must be a multiple of 16"
+            slots = self.store.put_parts(fb)
+        seq0 = self._part_head
+        self._part_head += n_frames
+        slots = slots.astype(np.int64)
+        # n-step windows: experience starting at s covers [s, e], e = min(s+n-1, episode end)
+        n = self.num_steps
+        nxt_term = np.full(T + 1, T + n, dtype=np.int64)  # next terminal step at or after t
+        for t in range(T - 1, -1, -1):
+            nxt_term[t] = t if terminals[t] else nxt_term[t + 1]
+        starts = np.arange(T, dtype=np.int64)
+        ends = np.minimum(starts + n - 1, nxt_term[:T])
+        keep = ends <= T - 1
+        starts, ends = starts[keep], ends[keep]
+        m = len(starts)
+        lens = (ends - starts + 1).astype(np.uint8)
+        offs = np.arange(stack, dtype=np.int64)
+        sp = slots[starts[:, None] + offs[None, :]].astype(np.int32)
+        nx = slots[ends[:, None] + 1 + offs[None, :]].astype(np.int32)
+        rw = np.zeros((m, n), dtype=np.float64)
+        rewards = np.asarray(rewards, dtype=np.float64)
+        for i in range(n):
+            ok = starts + i <= ends
+            rw[ok, i] = rewards[starts[ok] + i]
+        term = terminals[ends].astype(np.uint8)
+        act = np.stack([lay._action_array(a) for a in np.asarray(actions)[starts]]) \
+            if lay.action_shape != () else np.asarray(actions, dtype=lay.action_dtype)[starts]
+        cap = self._alloc_capacity
+        for lo in range(0, m, cap):
+            hi = min(m, lo + cap)
+            self.store.append(sp[lo:hi], nx[lo:hi], np.ascontiguousarray(act[lo:hi]),
+                              rw[lo:hi], lens[lo:hi], term[lo:hi])
+        self._n_total += m
+        self._live_min_seq.extend((seq0 + starts).tolist())
+        while len(self._live_min_seq) > cap:
+            self._live_min_seq.popleft()
+        return m
+
+    _traj_stack = 4
+
     # -- internals ----------------------------------------------------------
     def _create_store(self, state, action):
         self.layout = lay = _Layout(state, action)
@@ -333,9 +414,14 @@ class DeviceNStepBuffer:
                       action_shape=lay.action_shape, want_steps=want_steps)
         gp = self._gamma_pow(gamma)
         if mode == _lib.OBS_U8_TO_F32:
-            assert lay.torch_obs_dtype() == torch.uint8 and lay.part_nbytes == lay.part_bytes
+            assert lay.torch_obs_dtype() == torch.uint8
+            padded = lay.part_nbytes != lay.part_bytes
             out = self.store.gather(exps.n, gp, obs_mode=mode, obs_scale=phi.b2rl_obs_scale,
-                                    obs_shape=lay.obs_shape, **common)
+                                    obs_shape=None if padded else lay.obs_shape, **common)
+            if padded:  # parts are padded to 16 B in the ring: drop the pad columns
+                for k in ("state", "next_state"):
+                    t = out[k].view(exps.n, lay.stack, lay.part_bytes)[:, :, :lay.part_nbytes]
+                    out[k] = t.contiguous().view((exps.n,) + tuple(lay.obs_shape))
         else:
             out = self.store.gather(exps.n, gp, obs_mode=_lib.OBS_RAW, **common)
             for k in ("state", "next_state"):
