@@ -7,10 +7,10 @@
 //
 // Traffic per sampled experience (Atari, f32 out): up to 2*stack parts read
 // (7 056 B each, the shared ones hit L2) and 2*stack*part_bytes*4 B written.
-// The kernel is a pure stream: one CTA per (experience, side, part); every
-// thread turns one 32-bit word of the part (4 pixels) into one 128-bit store,
-// so both the loads (128 B per warp instruction) and the stores (512 B per
-// warp instruction) are fully coalesced.
+// The kernel is a pure stream: every thread turns one 32-bit word of a part
+// (4 pixels) into one 128-bit store, so both the loads (128 B per warp
+// instruction) and the stores (512 B per warp instruction) are fully
+// coalesced.
 #include <math.h>
 
 #include "b2rl_internal.cuh"
@@ -24,7 +24,7 @@ struct GatherArgs {
     const B2rlDevState *st;
     const int32_t *slots;      // slots of the last sample, or null
     const long long *index;    // logical indices, or null
-    const double *gamma_pow;   // [n_step + 1]
+    double gamma_pow[9];       // gamma**i, i <= n_step (<= 8), passed by value
     long long nslots;
     int n, stack, part_bytes, n_step, action_bytes;
     int obs_mode;
@@ -41,47 +41,66 @@ __device__ __forceinline__ long long gather_slot(const GatherArgs &a, int k)
     return (a.st->npop + a.index[k]) & (a.nslots - 1);
 }
 
-// blockIdx.x enumerates (k, side, part); the tail blocks do the scalars.
+// Grid: one CTA per (experience, side, part, piece) -- each part is cut in
+// GATHER_SPLIT pieces so that the CTAs are short (~17 KB of traffic) and the
+// last, partially filled wave costs little; the slot / part-index lookups are
+// done once per CTA.  The first `tail` CTAs additionally emit the scalars.
+#define GATHER_SPLIT 2
+
 __global__ void __launch_bounds__(256) k_gather(GatherArgs a)
 {
-    const int items = a.n * 2 * a.stack;
+    const int items = a.n * 2 * a.stack * GATHER_SPLIT;
     const int b = blockIdx.x;
     if (b < items) {
-        const int part = b % a.stack;
-        const int side = (b / a.stack) & 1;
-        const int k = b / (2 * a.stack);
+        const int piece = b % GATHER_SPLIT;
+        const int item = b / GATHER_SPLIT;
+        const int part = item % a.stack;
+        const int side = (item / a.stack) & 1;
+        const int k = item / (2 * a.stack);
         uint8_t *out = side ? a.o_next : a.o_state;
-        if (!out) return;
-        const long long slot = gather_slot(a, k);
-        const int32_t ps = (side ? a.next_parts : a.state_parts)[slot * a.stack + part];
-        const uint8_t *src = a.parts + (size_t)ps * a.part_bytes;
-        if (a.obs_mode == B2RL_OBS_U8_TO_F32) {
-            const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
-            float4 *d4 = reinterpret_cast<float4 *>(out) +
-                         ((size_t)k * a.stack + part) * (a.part_bytes / 4);
-            const int words = a.part_bytes / 4;
-            const float sc = a.obs_scale;
-#pragma unroll 4
-            for (int w = threadIdx.x; w < words; w += blockDim.x) {
-                const uint32_t v = __ldg(s4 + w);
-                float4 f;
-                f.x = (float)(v & 0xffu) * sc;
-                f.y = (float)((v >> 8) & 0xffu) * sc;
-                f.z = (float)((v >> 16) & 0xffu) * sc;
-                f.w = (float)(v >> 24) * sc;
-                __stcs(d4 + w, f);
+        if (out) {
+            const long long slot = gather_slot(a, k);
+            const int32_t ps = (side ? a.next_parts : a.state_parts)[slot * a.stack + part];
+            const uint8_t *src = a.parts + (size_t)ps * a.part_bytes;
+            if (a.obs_mode == B2RL_OBS_U8_TO_F32) {
+                const int words = a.part_bytes / 4;
+                const int per = (words + GATHER_SPLIT - 1) / GATHER_SPLIT;
+                const int w0 = piece * per;
+                const int w1 = min(words, w0 + per);
+                const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
+                float4 *d4 = reinterpret_cast<float4 *>(out) +
+                             ((size_t)k * a.stack + part) * words;
+                const float sc = a.obs_scale;
+                constexpr int U = 4; // loads in flight per thread
+                for (int base = w0 + threadIdx.x; base < w1; base += U * 256) {
+                    uint32_t v[U];
+#pragma unroll
+                    for (int i = 0; i < U; i++)
+                        if (base + i * 256 < w1) v[i] = __ldg(s4 + base + i * 256);
+#pragma unroll
+                    for (int i = 0; i < U; i++) {
+                        if (base + i * 256 >= w1) continue;
+                        float4 f;
+                        f.x = (float)(v[i] & 0xffu) * sc;
+                        f.y = (float)((v[i] >> 8) & 0xffu) * sc;
+                        f.z = (float)((v[i] >> 16) & 0xffu) * sc;
+                        f.w = (float)(v[i] >> 24) * sc;
+                        __stcs(d4 + base + i * 256, f);
+                    }
+                }
+            } else {
+                const int vecs = a.part_bytes / 16;
+                const int per = (vecs + GATHER_SPLIT - 1) / GATHER_SPLIT;
+                const int w0 = piece * per;
+                const int w1 = min(vecs, w0 + per);
+                const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
+                uint4 *d16 = reinterpret_cast<uint4 *>(out) + ((size_t)k * a.stack + part) * vecs;
+                for (int w = w0 + threadIdx.x; w < w1; w += 256) __stcs(d16 + w, __ldg(s16 + w));
             }
-        } else {
-            const uint4 *s16 = reinterpret_cast<const uint4 *>(src);
-            uint4 *d16 = reinterpret_cast<uint4 *>(out) +
-                         ((size_t)k * a.stack + part) * (a.part_bytes / 16);
-            const int vecs = a.part_bytes / 16;
-            for (int w = threadIdx.x; w < vecs; w += blockDim.x) __stcs(d16 + w, __ldg(s16 + w));
         }
-        return;
     }
     // scalar tail: one thread per experience
-    const int k = (b - items) * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.n) return;
     const long long slot = gather_slot(a, k);
     const int len = a.len[slot];
@@ -127,8 +146,6 @@ extern "C" int b2rl_replay_gather(b2rl_replay *h, const int64_t *index_dev, int3
     cudaStream_t s = (cudaStream_t)stream;
     B2RL_CUDA(cudaSetDevice(h->cfg.device));
     const b2rl_replay_config &c = h->cfg;
-    B2RL_CUDA(cudaMemcpyAsync(h->gamma_pow_dev, gamma_pow_host, sizeof(double) * (c.n_step + 1),
-                              cudaMemcpyHostToDevice, s));
     GatherArgs a;
     a.parts = h->parts;
     a.state_parts = h->state_parts;
@@ -140,7 +157,7 @@ extern "C" int b2rl_replay_gather(b2rl_replay *h, const int64_t *index_dev, int3
     a.st = h->st;
     a.slots = index_dev ? nullptr : h->last_slots;
     a.index = (const long long *)index_dev;
-    a.gamma_pow = h->gamma_pow_dev;
+    for (int i = 0; i <= c.n_step; i++) a.gamma_pow[i] = gamma_pow_host[i];
     a.nslots = h->nslots;
     a.n = n;
     a.stack = c.stack;
@@ -157,9 +174,10 @@ extern "C" int b2rl_replay_gather(b2rl_replay *h, const int64_t *index_dev, int3
     a.o_discount = out->discount;
     a.o_step_rewards = out->step_rewards;
     a.o_len = out->len;
-    const int items = n * 2 * c.stack;
     const int tail = (n + 255) / 256;
-    k_gather<<<items + tail, 256, 0, s>>>(a);
+    int grid = n * 2 * c.stack * GATHER_SPLIT;
+    if (grid < tail) grid = tail;
+    k_gather<<<grid, 256, 0, s>>>(a);
     B2RL_CUDA(cudaGetLastError());
     return B2RL_OK;
 }

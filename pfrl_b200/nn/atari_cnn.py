@@ -1,0 +1,44 @@
+"""Atari convolutional trunks (pfrl/nn/atari_cnn.py:17-82).  Plain PyTorch:
+these dense contractions are the only tensor-core work on the path and are
+served by cuDNN / cuBLAS."""
+import torch.nn as nn
+import torch.nn.functional as F
+
+from pfrl_b200.initializers import constant_bias_initializer, init_chainer_default
+
+
+class _AtariCNN(nn.Module):
+    def __init__(self, convs, flat, n_output_channels, activation, bias):
+        super().__init__()
+        self.activation = activation
+        self.n_output_channels = n_output_channels
+        self.layers = nn.ModuleList(convs)
+        self.output = nn.Linear(flat, n_output_channels)
+        self.apply(init_chainer_default)
+        self.apply(constant_bias_initializer(bias=bias))
+
+    def forward(self, state):
+        h = state
+        for conv in self.layers:
+            h = self.activation(conv(h))
+        return self.activation(self.output(h.reshape(h.shape[0], -1)))
+
+
+class LargeAtariCNN(_AtariCNN):
+    """Nature-DQN trunk: 8x8/4 -> 32, 4x4/2 -> 64, 3x3/1 -> 64, fc 3136 -> 512."""
+
+    def __init__(self, n_input_channels=4, n_output_channels=512, activation=F.relu, bias=0.1):
+        self.n_input_channels = n_input_channels
+        super().__init__(
+            [nn.Conv2d(n_input_channels, 32, 8, stride=4), nn.Conv2d(32, 64, 4, stride=2),
+             nn.Conv2d(64, 64, 3, stride=1)], 3136, n_output_channels, activation, bias)
+
+
+class SmallAtariCNN(_AtariCNN):
+    """NIPS-2013 DQN trunk: 8x8/4 -> 16, 4x4/2 -> 32, fc 2592 -> 256."""
+
+    def __init__(self, n_input_channels=4, n_output_channels=256, activation=F.relu, bias=0.1):
+        self.n_input_channels = n_input_channels
+        super().__init__(
+            [nn.Conv2d(n_input_channels, 16, 8, stride=4), nn.Conv2d(16, 32, 4, stride=2)],
+            2592, n_output_channels, activation, bias)
