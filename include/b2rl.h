@@ -216,6 +216,82 @@ int b2rl_replay_gather(b2rl_replay *h, const int64_t *index_dev, int32_t n,
                        float obs_scale, const b2rl_batch_out *out,
                        void *stream);
 
+/* ------------------------------------------------------------------------
+ * Fused loss kernels (fp32, device pointers, deterministic reductions).
+ * `mean` != 0: divide the batch sum by B ("mean" batch_accumulator).
+ * `weights` may be NULL (uniform replay).  `scratch` is B floats.
+ * ---------------------------------------------------------------------- */
+
+/* Categorical (C51 / Rainbow) loss: projects the next-state distribution
+ * next_p[B,n] through Tz = r + (1-terminal)*discount*z onto the support
+ * z[n], then cross-entropy with y[B,n].  Replaces
+ * _apply_categorical_projection (pfrl/agents/categorical_dqn.py:7-57) and
+ * CategoricalDQN._compute_loss (:178-204).  Outputs: t_out[B,n] projected
+ * target, delta_out[B] per-sample loss (the priority error), loss_out[1]. */
+int b2rl_c51_loss_fwd(const float *y, const float *next_p, const float *reward,
+                      const float *discount, const float *terminal,
+                      const float *weights, const float *z, int32_t B,
+                      int32_t n_atoms, int mean, float *t_out, float *delta_out,
+                      float *scratch, float *loss_out, void *stream);
+int b2rl_c51_loss_bwd(const float *y, const float *t, const float *weights,
+                      const float *grad_loss, int32_t B, int32_t n_atoms,
+                      int mean, float *grad_y, void *stream);
+
+/* Scalar TD loss: y = q[i, action[i]], t = r + discount*(1-terminal)*next_q,
+ * Huber(delta=1) if clip_delta else 0.5*(y-t)^2.  Replaces
+ * DQN._compute_target_values / _compute_loss and compute_[weighted_]value_loss
+ * (pfrl/agents/dqn.py:44-104, 388-470).  delta_out = |y - t|. */
+int b2rl_td_loss_fwd(const float *q, const int64_t *action, const float *next_q,
+                     const float *reward, const float *discount,
+                     const float *terminal, const float *weights, int32_t B,
+                     int32_t n_actions, int clip_delta, int mean, float *y_out,
+                     float *t_out, float *delta_out, float *scratch,
+                     float *loss_out, void *stream);
+int b2rl_td_loss_bwd(const float *y, const float *t, const float *weights,
+                     const int64_t *action, const float *grad_loss, int32_t B,
+                     int32_t n_actions, int clip_delta, int mean, float *grad_q,
+                     void *stream);
+
+/* Quantile Huber loss of IQN: |tau - 1[t<y]| * Huber(y, t) over [B, N, N'],
+ * mean over N', sum over N (compute_eltwise_huber_quantile_loss and the value
+ * losses of pfrl/agents/iqn.py:176-250); delta_out = mean over (N, N'). */
+int b2rl_quantile_huber_fwd(const float *y, const float *t, const float *taus,
+                            const float *weights, int32_t B, int32_t N,
+                            int32_t Np, int mean, float *delta_out,
+                            float *scratch, float *loss_out, void *stream);
+int b2rl_quantile_huber_bwd(const float *y, const float *t, const float *taus,
+                            const float *weights, const float *grad_loss,
+                            int32_t B, int32_t N, int32_t Np, int mean,
+                            float *grad_y, void *stream);
+
+/* ------------------------------------------------------------------------
+ * PPO: generalised advantage estimation over a time-major rollout [T, E] and
+ * the clipped-surrogate loss (forward value and gradients in one launch).
+ * ---------------------------------------------------------------------- */
+
+/* GAE, replaces _add_advantage_and_value_target_to_episode(s)
+ * (pfrl/agents/ppo.py:36-53) and the std_mean of :476-478.
+ * cut[t,e] = 1 marks the last transition of an episode segment (done, reset
+ * or flush); valid (may be NULL) masks unused slots.  scratch: 3 doubles per
+ * 128 environments.  stats[2] = mean, std (unbiased=False) of adv. */
+int b2rl_gae(const float *reward, const float *nonterminal, const float *v,
+             const float *v_next, const uint8_t *cut, const uint8_t *valid,
+             int32_t T, int32_t E, double gamma, double lambda, float *adv,
+             float *v_teacher, double *scratch, float *stats, void *stream);
+
+/* PPO._lossfun (pfrl/agents/ppo.py:634-671) + the advantage standardisation
+ * of :495 (adv_stats = {mean, std} or NULL).  clip_eps_vf < 0 selects the
+ * unclipped value loss.  Outputs d loss/d{log_prob, entropy, v_pred} and
+ * losses[4] = {total, policy, value, entropy}.  scratch: 3 doubles per 256
+ * samples. */
+int b2rl_ppo_loss(const float *log_prob, const float *entropy,
+                  const float *v_pred, const float *log_prob_old,
+                  const float *v_pred_old, const float *adv,
+                  const float *v_teacher, const float *adv_stats, int32_t M,
+                  float clip_eps, float clip_eps_vf, float value_coef,
+                  float entropy_coef, float *g_log_prob, float *g_entropy,
+                  float *g_v_pred, double *scratch, float *losses, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,162 @@
+"""Golden vectors for the loss / GAE kernels, produced by the REAL reference
+(called from oracle/gen_golden.py; TEST INFRASTRUCTURE ONLY)."""
+import os
+
+import numpy as np
+
+
+def main(out_dir):
+    import torch
+    from pfrl.agents import categorical_dqn, dqn, iqn, ppo
+
+    rng = np.random.RandomState(2024)
+    g = {}
+
+    # ---- scalar TD loss (dqn.py:44-104, 388-470) --------------------------------
+    B, nA = 96, 18
+    q = rng.randn(B, nA).astype(np.float32) * 2
+    act = rng.randint(0, nA, size=B)
+    next_q = rng.randn(B).astype(np.float32) * 2
+    rew = rng.choice([-1.0, 0.0, 1.0, 2.5], size=B).astype(np.float32)
+    disc = (0.99 ** rng.randint(1, 4, size=B)).astype(np.float32)
+    term = (rng.rand(B) < 0.2).astype(np.float32)
+    w = (rng.rand(B) + 0.1).astype(np.float32)
+    g.update(td_q=q, td_action=act, td_next_q=next_q, td_reward=rew, td_discount=disc,
+             td_terminal=term, td_weights=w)
+    for clip in (True, False):
+        for acc in ("mean", "sum"):
+            for use_w in (True, False):
+                qt = torch.tensor(q, requires_grad=True)
+                y = qt[torch.arange(B), torch.tensor(act)]
+                t = torch.tensor(rew) + torch.tensor(disc) * (1.0 - torch.tensor(term)) * \
+                    torch.tensor(next_q)
+                if use_w:
+                    loss = dqn.compute_weighted_value_loss(y, t, torch.tensor(w), clip, acc)
+                else:
+                    loss = dqn.compute_value_loss(y, t, clip, acc)
+                loss.backward()
+                key = "td_%d_%s_%d" % (clip, acc, use_w)
+                g[key + "_loss"] = loss.detach().numpy()
+                g[key + "_grad"] = qt.grad.numpy()
+    g["td_delta"] = np.abs(q[np.arange(B), act] - (rew + disc * (1 - term) * next_q))
+
+    # ---- C51 (categorical_dqn.py:7-57, 60-97, 178-204) --------------------------
+    B, n = 80, 51
+    z = torch.linspace(-10, 10, n, dtype=torch.float32)
+    logits = rng.randn(B, n).astype(np.float32)
+    y = torch.softmax(torch.tensor(logits), dim=1)
+    next_p = torch.softmax(torch.tensor(rng.randn(B, n).astype(np.float32) * 2), dim=1)
+    rew = rng.choice([-1.0, 0.0, 1.0, 3.0, -12.0, 15.0], size=B).astype(np.float32)
+    disc = (0.99 ** rng.randint(1, 4, size=B)).astype(np.float32)
+    term = (rng.rand(B) < 0.25).astype(np.float32)
+    w = (rng.rand(B) + 0.1).astype(np.float32)
+    Tz = (torch.tensor(rew)[..., None] + (1.0 - torch.tensor(term)[..., None])
+          * torch.tensor(disc)[..., None] * z[None])
+    t = categorical_dqn._apply_categorical_projection(Tz, next_p, z)
+    g.update(c51_z=z.numpy(), c51_y=y.numpy(), c51_next_p=next_p.numpy(), c51_reward=rew,
+             c51_discount=disc, c51_terminal=term, c51_weights=w, c51_target=t.numpy())
+    for acc in ("mean", "sum"):
+        for use_w in (True, False):
+            yt = y.clone().requires_grad_(True)
+            elt = -t * torch.log(torch.clamp(yt, 1e-10, 1.0))
+            if use_w:
+                loss = categorical_dqn.compute_weighted_value_loss(elt, B, torch.tensor(w), acc)
+            else:
+                loss = categorical_dqn.compute_value_loss(elt, acc)
+            loss.backward()
+            key = "c51_%s_%d" % (acc, use_w)
+            g[key + "_loss"] = loss.detach().numpy()
+            g[key + "_grad"] = yt.grad.numpy()
+            g["c51_delta"] = elt.detach().sum(dim=1).numpy()
+    # a hand-checkable projection case incl. inexact delta_z and out-of-range atoms
+    z2 = torch.linspace(-1, 1, 7, dtype=torch.float32)
+    yv = torch.tensor([[-3.0, -1.0, -0.2, 0.0, 1.0 / 3, 0.999, 5.0]], dtype=torch.float32)
+    pv = torch.tensor([[0.1, 0.2, 0.05, 0.25, 0.1, 0.2, 0.1]], dtype=torch.float32)
+    g.update(proj_z=z2.numpy(), proj_y=yv.numpy(), proj_p=pv.numpy(),
+             proj_out=categorical_dqn._apply_categorical_projection(yv, pv, z2).numpy())
+
+    # ---- quantile Huber (iqn.py:176-250) ----------------------------------------
+    B, N, Np = 24, 16, 12
+    yq = rng.randn(B, N).astype(np.float32)
+    tq = (rng.randn(B, Np) * 1.5).astype(np.float32)
+    taus = rng.rand(B, N).astype(np.float32)
+    w = (rng.rand(B) + 0.1).astype(np.float32)
+    g.update(qh_y=yq, qh_t=tq, qh_taus=taus, qh_weights=w)
+    for acc in ("mean", "sum"):
+        for use_w in (True, False):
+            yt = torch.tensor(yq, requires_grad=True)
+            elt = iqn.compute_eltwise_huber_quantile_loss(yt, torch.tensor(tq), torch.tensor(taus))
+            if use_w:
+                loss = iqn.compute_weighted_value_loss(elt, torch.tensor(w), acc)
+            else:
+                loss = iqn.compute_value_loss(elt, acc)
+            loss.backward()
+            key = "qh_%s_%d" % (acc, use_w)
+            g[key + "_loss"] = loss.detach().numpy()
+            g[key + "_grad"] = yt.grad.numpy()
+            g["qh_delta"] = elt.detach().mean((1, 2)).numpy()
+
+    # ---- GAE (ppo.py:36-53): episodes of Python-float transitions --------------
+    T, E = 40, 6
+    rew = rng.randn(T, E)
+    v = rng.randn(T, E).astype(np.float32)
+    v_next = rng.randn(T, E).astype(np.float32)
+    nonterm = (rng.rand(T, E) > 0.1).astype(np.float64)
+    cut = (nonterm == 0) | (rng.rand(T, E) < 0.05)
+    cut[-1, :] = True
+    adv = np.zeros((T, E))
+    vt = np.zeros((T, E))
+    for gamma, lambd, tag in ((0.995, 0.95, "a"), (0.9, 0.5, "b"), (1.0, 1.0, "c")):
+        for e in range(E):
+            start = 0
+            for tt in range(T):
+                if cut[tt, e]:
+                    ep = [dict(reward=float(rew[k, e]), nonterminal=float(nonterm[k, e]),
+                               v_pred=float(v[k, e]), next_v_pred=float(v_next[k, e]))
+                          for k in range(start, tt + 1)]
+                    ppo._add_advantage_and_value_target_to_episode(ep, gamma, lambd)
+                    for k, tr in zip(range(start, tt + 1), ep):
+                        adv[k, e] = tr["adv"]
+                        vt[k, e] = tr["v_teacher"]
+                    start = tt + 1
+        g["gae_%s_adv" % tag] = adv.copy()
+        g["gae_%s_vt" % tag] = vt.copy()
+        g["gae_%s_params" % tag] = np.array([gamma, lambd])
+    g.update(gae_reward=rew, gae_v=v, gae_v_next=v_next, gae_nonterminal=nonterm, gae_cut=cut)
+
+    # ---- PPO loss (ppo.py:495, 634-671) through a real PPO instance -------------
+    M = 200
+    lp = (rng.randn(M) * 0.3 - 1.0).astype(np.float32)
+    lp_old = (lp + rng.randn(M).astype(np.float32) * 0.25).astype(np.float32)
+    ent = (rng.rand(M) + 0.5).astype(np.float32)
+    vp = rng.randn(M, 1).astype(np.float32)
+    vp_old = (vp + rng.randn(M, 1).astype(np.float32) * 0.3).astype(np.float32)
+    vteach = rng.randn(M, 1).astype(np.float32)
+    advs = rng.randn(M).astype(np.float32) * 2 + 0.3
+    g.update(ppo_lp=lp, ppo_lp_old=lp_old, ppo_ent=ent, ppo_v=vp, ppo_v_old=vp_old,
+             ppo_vt=vteach, ppo_adv=advs)
+    model = torch.nn.Linear(2, 2)
+    for clip_vf, tag in ((None, "a"), (0.2, "b")):
+        agent = ppo.PPO(model, torch.optim.SGD(model.parameters(), lr=0.1), clip_eps=0.2,
+                        clip_eps_vf=clip_vf, value_func_coef=0.5, entropy_coef=0.01)
+        all_advs = torch.tensor(advs)
+        std_a, mean_a = torch.std_mean(all_advs, unbiased=False)
+        a_n = (all_advs - mean_a) / (std_a + 1e-8)
+        t_lp = torch.tensor(lp, requires_grad=True)
+        t_ent = torch.tensor(ent, requires_grad=True)
+        t_v = torch.tensor(vp, requires_grad=True)
+        loss = agent._lossfun(t_ent, t_v, t_lp, vs_pred_old=torch.tensor(vp_old),
+                              log_probs_old=torch.tensor(lp_old), advs=a_n,
+                              vs_teacher=torch.tensor(vteach))
+        loss.backward()
+        g["ppo_%s_loss" % tag] = loss.detach().numpy()
+        g["ppo_%s_policy" % tag] = np.float32(agent.policy_loss_record[-1])
+        g["ppo_%s_value" % tag] = np.float32(agent.value_loss_record[-1])
+        g["ppo_%s_g_lp" % tag] = t_lp.grad.numpy()
+        g["ppo_%s_g_ent" % tag] = t_ent.grad.numpy()
+        g["ppo_%s_g_v" % tag] = t_v.grad.numpy()
+        g["ppo_mean_std"] = np.array([float(mean_a), float(std_a)], dtype=np.float32)
+
+    g["numpy_version"] = np.array(np.__version__)
+    np.savez_compressed(os.path.join(out_dir, "losses.npz"), **g)
+    print("wrote losses.npz with", len(g), "arrays")

@@ -2,3 +2,6 @@ from pfrl_b200.agents.categorical_double_dqn import CategoricalDoubleDQN  # NOQA
 from pfrl_b200.agents.categorical_dqn import CategoricalDQN  # NOQA
 from pfrl_b200.agents.double_dqn import DoubleDQN  # NOQA
 from pfrl_b200.agents.dqn import DQN  # NOQA
+from pfrl_b200.agents.iqn import IQN  # NOQA
+from pfrl_b200.agents.ppo import PPO  # NOQA
+from pfrl_b200.agents.soft_actor_critic import SoftActorCritic  # NOQA

@@ -25,6 +25,7 @@ import torch
 import torch.nn.functional as F
 
 from pfrl_b200 import agent
+from pfrl_b200.ops import losses as fused
 from pfrl_b200.replay_buffer import ReplayUpdater, batch_experiences
 from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
 from pfrl_b200.utils import clip_l2_grad_norm_
@@ -213,11 +214,13 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
         self.optimizer.step()
         self.optim_t += 1
 
+    def _next_q(self, exp_batch):
+        """Value of the next state used in the target: max_a Q_target(s', a)."""
+        return self.target_model(exp_batch["next_state"]).max
+
     def _compute_target_values(self, exp_batch):
-        target_next_qout = self.target_model(exp_batch["next_state"])
-        next_q_max = target_next_qout.max
         return exp_batch["reward"] + exp_batch["discount"] * (
-            1.0 - exp_batch["is_state_terminal"]) * next_q_max
+            1.0 - exp_batch["is_state_terminal"]) * self._next_q(exp_batch)
 
     def _compute_y_and_t(self, exp_batch):
         batch_size = exp_batch["reward"].shape[0]
@@ -227,8 +230,23 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
             batch_q_target = torch.reshape(self._compute_target_values(exp_batch), (batch_size, 1))
         return batch_q, batch_q_target
 
+    use_fused_loss = True
+
     def _compute_loss(self, exp_batch, want_errors=False):
         """Returns (loss, per-sample |y - t| or None); dqn.py:432-470."""
+        if self.use_fused_loss and exp_batch["reward"].is_cuda:
+            # one fused kernel: gather Q(s)[a], TD target, |y - t|, Huber / MSE,
+            # importance weights and the deterministic batch reduction
+            qout = self.model(exp_batch["state"])
+            with torch.no_grad():
+                next_q = self._next_q(exp_batch)
+            loss, delta, y, _ = fused.td_loss(
+                qout.q_values, exp_batch["action"], next_q, exp_batch["reward"],
+                exp_batch["discount"], exp_batch["is_state_terminal"],
+                exp_batch.get("weights"), clip_delta=self.clip_delta,
+                mean=self.batch_accumulator == "mean")
+            self.q_record.extend(y)
+            return loss, delta
         y, t = self._compute_y_and_t(exp_batch)
         self.q_record.extend(y)
         delta = None

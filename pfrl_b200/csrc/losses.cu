@@ -26,8 +26,8 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // Deterministic final reduction: the last CTA to arrive sums term[i] for
-// i < n in a fixed order and writes *out = sum * scale.
-__device__ void finish_sum(const float *term, int n, float scale, float *out, float *sh)
+// i < n in a fixed order and writes *out = sum / divisor.
+__device__ void finish_sum(const float *term, int n, float divisor, float *out, float *sh)
 {
     __shared__ bool last;
     __threadfence();
@@ -47,7 +47,7 @@ __device__ void finish_sum(const float *term, int n, float scale, float *out, fl
     if (threadIdx.x < 32) {
         s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
         s = warp_sum(s);
-        if (threadIdx.x == 0) *out = s * scale;
+        if (threadIdx.x == 0) *out = __fdiv_rn(s, divisor);
     }
 }
 
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(C51_WARPS * 32) k_c51_fwd(C51Args a)
             a.term[i] = a.weights ? __fmul_rn(acc, a.weights[i]) : acc;
         }
     }
-    finish_sum(a.term, a.B, a.mean ? 1.0f / (float)a.B : 1.0f, a.loss_out, sh);
+    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh);
 }
 
 struct C51BwdArgs {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) k_td_fwd(TdArgs a)
         a.delta_out[i] = ad;
         a.term[i] = a.weights ? __fmul_rn(l, a.weights[i]) : l;
     }
-    finish_sum(a.term, a.B, a.mean ? 1.0f / (float)a.B : 1.0f, a.loss_out, sh);
+    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh);
 }
 
 struct TdBwdArgs {
@@ -233,13 +233,12 @@ __global__ void __launch_bounds__(256) k_qh_fwd(QhArgs a)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        // loss per sample: mean over N' then sum over N (iqn.py:392-395);
-        // the reported error is the same quantity
+        // loss per sample: mean over N' then sum over N (iqn.py:210-250)
         const float li = s_tot / (float)a.Np;
-        a.delta_out[i] = li;
+        a.delta_out[i] = s_tot / (float)(a.N * a.Np); // eltwise_loss.mean((1, 2)), iqn.py:388
         a.term[i] = a.weights ? __fmul_rn(li, a.weights[i]) : li;
     }
-    finish_sum(a.term, a.B, a.mean ? 1.0f / (float)a.B : 1.0f, a.loss_out, sh);
+    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh);
 }
 
 struct QhBwdArgs {

@@ -1,0 +1,5 @@
+from pfrl_b200.envs.serial_vector_env import SerialVectorEnv  # NOQA
+from pfrl_b200.envs.synthetic import DeviceObsList  # NOQA
+from pfrl_b200.envs.synthetic import SyntheticAtariVectorEnv  # NOQA
+from pfrl_b200.envs.synthetic import SyntheticContinuousVectorEnv  # NOQA
+from pfrl_b200.envs.toy import ChainEnv  # NOQA

@@ -1,0 +1,124 @@
+"""Synchronous vector-env training loop.
+
+Same contract as pfrl/experiments/train_agent_batch.py:10-263 (pinned by the
+reference's tests/experiments_tests/test_train_agent_batch.py): the per-env
+step counter ``t`` advances by ``num_envs`` per vector step, hooks run once
+per env step with their ``t``, checkpoints at multiples of checkpoint_freq,
+``resets`` from max_episode_len or ``info["needs_reset"]``, the agent is saved
+as ``<t>_finish`` / ``<t>_except``, and ``env.reset(mask)`` restarts only the
+finished environments.
+"""
+import logging
+import os
+from collections import deque
+
+import numpy as np
+
+from pfrl_b200.experiments.evaluator import Evaluator, save_agent
+
+
+def _to_host(x, dtype):
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, dtype=dtype)
+
+
+def train_agent_batch(agent, env, steps, outdir, checkpoint_freq=None, log_interval=None,
+                      max_episode_len=None, step_offset=0, evaluator=None,
+                      successful_score=None, step_hooks=(), return_window_size=100,
+                      logger=None):
+    """Train ``agent`` on the vector env ``env`` for ``steps`` env steps.
+    Returns the list of evaluation statistics dicts."""
+    logger = logger or logging.getLogger(__name__)
+    recent_returns = deque(maxlen=return_window_size)
+    num_envs = env.num_envs
+    episode_r = np.zeros(num_envs, dtype=np.float64)
+    episode_idx = np.zeros(num_envs, dtype="i")
+    episode_len = np.zeros(num_envs, dtype="i")
+
+    obss = env.reset()
+    t = step_offset
+    if hasattr(agent, "t"):
+        agent.t = step_offset
+    eval_stats_history = []
+    try:
+        while True:
+            actions = agent.batch_act(obss)
+            obss, rs, dones, infos = env.step(actions)
+            rs = _to_host(rs, np.float64)
+            dones = _to_host(dones, bool)
+            episode_r += rs
+            episode_len += 1
+
+            if max_episode_len is None:
+                resets = np.zeros(num_envs, dtype=bool)
+            else:
+                resets = episode_len == max_episode_len
+            resets = np.logical_or(resets, [info.get("needs_reset", False) for info in infos])
+            agent.batch_observe(obss, rs, dones, resets)
+
+            end = np.logical_or(resets, dones)
+            not_end = np.logical_not(end)
+            episode_idx += end
+            recent_returns.extend(episode_r[end])
+
+            for _ in range(num_envs):
+                t += 1
+                if checkpoint_freq and t % checkpoint_freq == 0:
+                    save_agent(agent, t, outdir, logger, suffix="_checkpoint")
+                for hook in step_hooks:
+                    hook(env, agent, t)
+
+            if log_interval is not None and t >= log_interval and t % log_interval < num_envs:
+                logger.info(
+                    "outdir:%s step:%s episode:%s last_R: %s average_R:%s", outdir, t,
+                    np.sum(episode_idx), recent_returns[-1] if recent_returns else np.nan,
+                    np.mean(recent_returns) if recent_returns else np.nan)
+                logger.info("statistics: %s", agent.get_statistics())
+            if evaluator:
+                eval_score = evaluator.evaluate_if_necessary(t=t, episodes=np.sum(episode_idx))
+                if eval_score is not None:
+                    eval_stats = dict(agent.get_statistics())
+                    eval_stats["eval_score"] = eval_score
+                    eval_stats_history.append(eval_stats)
+                    if successful_score is not None and evaluator.max_score >= successful_score:
+                        break
+            if t >= steps:
+                break
+            episode_r[end] = 0
+            episode_len[end] = 0
+            obss = env.reset(not_end)
+    except (Exception, KeyboardInterrupt):
+        save_agent(agent, t, outdir, logger, suffix="_except")
+        env.close()
+        if evaluator:
+            evaluator.env.close()
+        raise
+    else:
+        save_agent(agent, t, outdir, logger, suffix="_finish")
+    return eval_stats_history
+
+
+def train_agent_batch_with_evaluation(
+        agent, env, steps, eval_n_steps, eval_n_episodes, eval_interval, outdir,
+        checkpoint_freq=None, max_episode_len=None, step_offset=0, eval_max_episode_len=None,
+        return_window_size=100, eval_env=None, log_interval=None, successful_score=None,
+        step_hooks=(), save_best_so_far_agent=True, logger=None):
+    """train_agent_batch + periodic evaluation; returns (agent, history)."""
+    logger = logger or logging.getLogger(__name__)
+    os.makedirs(outdir, exist_ok=True)
+    if eval_env is None:
+        eval_env = env
+    if eval_max_episode_len is None:
+        eval_max_episode_len = max_episode_len
+    evaluator = Evaluator(
+        agent=agent, n_steps=eval_n_steps, n_episodes=eval_n_episodes,
+        eval_interval=eval_interval, outdir=outdir, max_episode_len=eval_max_episode_len,
+        env=eval_env, step_offset=step_offset, save_best_so_far_agent=save_best_so_far_agent,
+        logger=logger)
+    history = train_agent_batch(
+        agent, env, steps, outdir, checkpoint_freq=checkpoint_freq,
+        max_episode_len=max_episode_len, step_offset=step_offset, evaluator=evaluator,
+        successful_score=successful_score, return_window_size=return_window_size,
+        log_interval=log_interval, step_hooks=step_hooks, logger=logger)
+    return agent, history

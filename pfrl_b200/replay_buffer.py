@@ -51,7 +51,10 @@ class AbstractReplayBuffer(object, metaclass=ABCMeta):
 def _register_device_buffers():
     from pfrl_b200.replay_buffers import device_buffer
 
+    from pfrl_b200.replay_buffers import host
+
     AbstractReplayBuffer.register(device_buffer.DeviceNStepBuffer)
+    AbstractReplayBuffer.register(host.HostReplayBuffer)
 
 
 _register_device_buffers()

@@ -21,6 +21,9 @@ def _move(batched, device):
 
 def batch_states(states, device, phi):
     # device-resident batch (one tensor holding every env's observation)
+    whole = getattr(states, "batch", None)
+    if isinstance(whole, torch.Tensor) and whole.is_cuda:
+        states = whole
     if isinstance(states, torch.Tensor) and states.is_cuda:
         mode = getattr(phi, "b2rl_obs_mode", None)
         if mode == 1:
