@@ -131,7 +131,7 @@ def cpu_reference_run(capacity, batch, steps, warmup, seconds=None, pool=65536, 
     from oracle.pyport import PyPrioritizedReplayBuffer, py_batch_experiences
     from pfrl_b200.utils.lazy_frames import LazyFrames
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(min(16, os.cpu_count() or 1))  # collate only; the replay code is 1 thread
     rng = np.random.RandomState(seed)
     pool = min(pool, capacity + STACK + N_STEP)
     frames = rng.randint(0, 256, size=(pool, 1) + FRAME, dtype=np.uint8)
@@ -178,6 +178,119 @@ def cpu_reference_run(capacity, batch, steps, warmup, seconds=None, pool=65536, 
 
 
 # ---------------------------------------------------------------------------
+# Rainbow end-to-end training loop (train_agent_batch's inner loop, untimed
+# bookkeeping stripped): act -> env.step -> observe (append / sample / update)
+# ---------------------------------------------------------------------------
+RAINBOW_ENVS = 16
+RAINBOW_UPDATE_INTERVAL = 4
+
+
+def make_rainbow_agent(buf, dev_index, batch, grad_sync=None):
+    import torch
+    from pfrl_b200 import agents, explorers, nn as pnn, parallel, q_functions
+    from pfrl_b200.utils.phi import ScaleU8
+
+    torch.manual_seed(0)
+    q = q_functions.DistributionalDuelingDQN(18, 51, -10, 10)
+    pnn.to_factorized_noisy(q, sigma_scale=0.5)
+    opt = torch.optim.Adam(q.parameters(), 6.25e-5, eps=1.5e-4)
+    agent = agents.CategoricalDoubleDQN(
+        q, opt, buf, gpu=dev_index, gamma=GAMMA, explorer=explorers.Greedy(),
+        minibatch_size=batch, replay_start_size=batch, target_update_interval=32000,
+        update_interval=RAINBOW_UPDATE_INTERVAL, batch_accumulator="mean", phi=ScaleU8(),
+        grad_sync=grad_sync)
+    parallel.broadcast_parameters(agent.model)
+    parallel.broadcast_parameters(agent.target_model)
+    return agent
+
+
+def rainbow_loop(agent, env, vec_steps):
+    obss = env.reset()
+    for _ in range(vec_steps):
+        actions = agent.batch_act(obss)
+        obss, rs, dones, infos = env.step(actions)
+        resets = np.zeros(env.num_envs, dtype=bool)
+        agent.batch_observe(obss, rs, dones, resets)
+        obss = env.reset(np.logical_not(dones))
+
+
+def best_torch_threads():
+    """Pick the intra-op thread count that makes the CPU baseline FASTEST
+    (all cores oversubscribes badly on shared 100+-core hosts): probe a
+    Rainbow-sized forward/backward at a few counts and keep the best."""
+    import torch
+    from oracle.pyport_rainbow import RainbowNet
+
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = sorted({c for c in (4, 8, 16, 32, 64, avail) if c <= avail})
+    net = RainbowNet()
+    x = torch.rand(32, 4, 84, 84)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            net(x).sum().backward()
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_rainbow_run(capacity, batch, seconds, num_envs=RAINBOW_ENVS, pool=65536, seed=0):
+    """CPU port of the same loop: pyport replay + plain-torch Rainbow update."""
+    import torch
+    from oracle.pyport import PyPrioritizedReplayBuffer
+    from oracle.pyport_rainbow import PyRainbow
+    from pfrl_b200.utils.lazy_frames import LazyFrames
+
+    best_torch_threads()
+    rng = np.random.RandomState(seed)
+    frames = rng.randint(0, 256, size=(pool, 1) + FRAME, dtype=np.uint8)
+    flist = [frames[i] for i in range(pool)]
+    buf = PyPrioritizedReplayBuffer(capacity, alpha=ALPHA, beta0=BETA0, betasteps=None,
+                                    num_steps=N_STEP, normalize_by_max="memory")
+    T = capacity + N_STEP - 1
+    obs = [LazyFrames([flist[(t + j) % pool] for j in range(STACK)], stack_axis=0)
+           for t in range(T + 1)]
+    trans = [dict(state=obs[t], action=int(t % 18), reward=float((t % 3) - 1),
+                  next_state=obs[t + 1], next_action=None, is_state_terminal=False)
+             for t in range(T)]
+    buf.memory.bulk_load([trans[s:s + N_STEP] for s in range(capacity)], rng.rand(capacity) + 0.05)
+    agent = PyRainbow(buf, GAMMA, batch)
+    np.random.seed(seed)
+    cur = [LazyFrames([flist[rng.randint(pool)]] * STACK, stack_axis=0) for _ in range(num_envs)]
+    t = 0
+    env_steps = 0
+    updates = 0
+
+    def vec_step():
+        nonlocal t, env_steps, updates
+        acts = agent.act(cur)
+        for i in range(num_envs):
+            nf = flist[rng.randint(pool)]
+            nxt = LazyFrames(cur[i]._frames[1:] + [nf], stack_axis=0)
+            t += 1
+            buf.append(cur[i], int(acts[i]), float(rng.randint(-1, 2)), nxt, None, False, env_id=i)
+            cur[i] = nxt
+            if t % RAINBOW_UPDATE_INTERVAL == 0:
+                agent.update()
+                updates += 1
+        env_steps += num_envs
+
+    vec_step()  # warm-up
+    env_steps = updates = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        vec_step()
+    dt = time.perf_counter() - t0
+    return {"env_steps_per_sec": env_steps / dt, "updates_per_sec": updates / dt,
+            "ms_per_update": 1e3 * dt / max(updates, 1), "seconds": dt, "num_envs": num_envs,
+            "threads": torch.get_num_threads()}
+
+
+# ---------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -188,6 +301,7 @@ def main():
         if rank != 0:
             return
         r = cpu_reference_run(args.capacity, args.batch, args.steps, args.warmup)
+        rb = None if args.no_rainbow else cpu_rainbow_run(args.capacity, args.batch, 20.0)
         line = {
             "impl": "reference", "metric": "replay_samples_per_sec", "value": r["samples_per_sec"],
             "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
@@ -202,6 +316,14 @@ def main():
             "e2e": {"value": r["samples_per_sec"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
         }
+        if rb is not None:
+            line["rainbow"] = {"env_steps_per_sec": rb["env_steps_per_sec"],
+                               "e2e_env_steps_per_sec": rb["env_steps_per_sec"],
+                               "updates_per_sec": rb["updates_per_sec"],
+                               "ms_per_update": rb["ms_per_update"], "num_envs": rb["num_envs"],
+                               "torch_threads": rb["threads"], "kind": "port",
+                               "sample": "%.0f s of act/append/sample(%d)/update on the host"
+                                         % (rb["seconds"], args.batch)}
         print(json.dumps(line))
         return
 
@@ -336,11 +458,38 @@ def main():
     ms_e2e = t2.elapsed_time(t3)
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- Rainbow training loop on the same shard ----------------------------------
+    rb = None
+    if not args.no_rainbow:
+        from pfrl_b200 import parallel
+        from pfrl_b200.envs import SyntheticAtariVectorEnv
+
+        torch.backends.cudnn.allow_tf32 = False  # fp32 parity configuration
+        torch.backends.cuda.matmul.allow_tf32 = False
+        agent = make_rainbow_agent(buf, local_rank, B,
+                                   grad_sync=parallel.GradSync() if world > 1 else None)
+        vec_steps = max(8, min(K, 40))
+        res = {}
+        for tag, env_dev in (("value", dev), ("e2e", "cpu")):
+            env = SyntheticAtariVectorEnv(RAINBOW_ENVS, device=env_dev, seed=11 + rank)
+            rainbow_loop(agent, env, 3)  # warm-up (cuDNN autotune, allocator)
+            barrier()
+            a, b = ev(), ev()
+            n0 = agent.optim_t
+            a.record()
+            rainbow_loop(agent, env, vec_steps)
+            b.record()
+            barrier()
+            res[tag] = (a.elapsed_time(b), agent.optim_t - n0)
+        rb = (res, vec_steps)
+
     # ---- max over ranks ---------------------------------------------------------
-    tm = torch.tensor([ms_value, ms_e2e], device=dev, dtype=torch.float64)
+    tm = torch.tensor([ms_value, ms_e2e] + ([rb[0]["value"][0], rb[0]["e2e"][0]] if rb else []),
+                      device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_value, ms_e2e = [float(x) for x in tm.tolist()]
+    tml = [float(x) for x in tm.tolist()]
+    ms_value, ms_e2e = tml[0], tml[1]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -379,7 +528,27 @@ def main():
         "clocks": clk, "prefill_s": fill_s,
         "hbm_bytes_per_rank": store.device_bytes,
     }
+    if rb is not None:
+        res, vec_steps = rb
+        steps_total = world * RAINBOW_ENVS * vec_steps
+        line["rainbow"] = {
+            "env_steps_per_sec": steps_total / (tml[2] / 1e3),
+            "e2e_env_steps_per_sec": steps_total / (tml[3] / 1e3),
+            "num_envs_per_rank": RAINBOW_ENVS, "vector_steps": vec_steps,
+            "updates": res["value"][1], "update_interval": RAINBOW_UPDATE_INTERVAL,
+            "ms_per_update_incl_acting": tml[2] / max(res["value"][1], 1),
+            "minibatch_per_rank": B, "dtype": "fp32 (TF32 off)",
+            "model": "DistributionalDuelingDQN(18, 51) + factorized noisy, Adam(6.25e-5)",
+            "note": "value: GPU-resident synthetic env; e2e: host numpy env (frames H2D, "
+                    "actions D2H); gradient all-reduce (NCCL) when n_gpus > 1"}
     if not args.no_cpu_baseline:
+        if rb is not None:
+            rc = cpu_rainbow_run(cap, B, 10.0)
+            line["rainbow"]["cpu_baseline"] = {
+                "value": rc["env_steps_per_sec"], "unit": "env-steps/s", "kind": "port",
+                "cores": rc["threads"], "ms_per_update": rc["ms_per_update"],
+                "sample": "%.0f s of the same loop on the host (oracle/pyport_rainbow.py)"
+                          % rc["seconds"]}
         r = cpu_reference_run(cap, B, 10 ** 9, 2, seconds=args.cpu_seconds)
         line["cpu_baseline"] = {
             "value": r["samples_per_sec"], "unit": "samples/s", "cores": 1, "kind": "port",

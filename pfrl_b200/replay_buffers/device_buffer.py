@@ -359,15 +359,23 @@ class DeviceNStepBuffer:
             return
         self._pend_parts = []
         lay = self.layout
-        if lay.on_device:
-            buf = torch.zeros((len(parts), lay.part_bytes), dtype=torch.uint8, device=self.device)
-            for i, p in enumerate(parts):
-                buf[i, :lay.part_nbytes] = p.contiguous().view(-1).view(torch.uint8)
-            slots = self.store.put_parts(buf)
+        on_dev = [isinstance(p, torch.Tensor) and p.is_cuda for p in parts]
+        if all(on_dev):
+            flat = torch.stack([p.reshape(-1) for p in parts]).view(torch.uint8)
+            if lay.part_nbytes != lay.part_bytes:
+                buf = torch.zeros((len(parts), lay.part_bytes), dtype=torch.uint8,
+                                  device=self.device)
+                buf[:, :lay.part_nbytes] = flat
+                flat = buf
+            slots = self.store.put_parts(flat.contiguous())
         else:
             buf = np.zeros((len(parts), lay.part_bytes), dtype=np.uint8)
+            np_dtype = lay.part_dtype if not isinstance(lay.part_dtype, torch.dtype) else \
+                torch.empty(0, dtype=lay.part_dtype).numpy().dtype
             for i, p in enumerate(parts):
-                a = np.ascontiguousarray(np.asarray(p, dtype=lay.part_dtype))
+                if isinstance(p, torch.Tensor):
+                    p = p.detach().cpu().numpy()
+                a = np.ascontiguousarray(np.asarray(p, dtype=np_dtype))
                 buf[i, :lay.part_nbytes] = a.reshape(-1).view(np.uint8)
             slots = self.store.put_parts(buf)
         expect = (self._part_head - len(parts)) % self._part_capacity
