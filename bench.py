@@ -506,6 +506,7 @@ def main():
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
     gather_bytes = ALGO_BYTES_GATHER * B
     achieved = gather_bytes / (kern_ms["gather"] * 1e-3) / 1e9
+    traffic = ncu_gather_traffic() if (B == 512 and args.capacity == 10 ** 6) else None
     line = {
         "metric": "replay_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_value / K, "higher_is_better": True,
@@ -517,7 +518,8 @@ def main():
         "gpu_launches": 4 * K,
         "kernels_ms": kern_ms,
         "roofline": {"bound": "hbm", "kernel": "k_gather", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "profiles/*_ncu_full_summary.csv (ncu --set full, per launch)",
                      "algorithmic_bytes_per_launch": gather_bytes, "peak_source": peak_src,
                      "kernel_ms": kern_ms["gather"],
                      "share_of_step": kern_ms["gather"] / (ms_value / K)},
@@ -559,6 +561,24 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_gather_traffic():
+    """dram__bytes_read + dram__bytes_write of k_gather per launch, from the
+    newest committed ncu --set full summary under profiles/ (bytes)."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")))
+    if not files:
+        return None
+    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for row in csv.reader(open(files[-1])):
+        if len(row) == 4 and row[0] == "gather" and row[1] in ("dram__bytes_read.sum",
+                                                             "dram__bytes_write.sum"):
+            total += float(row[2]) * mult.get(row[3], 1)
+    return total or None
 
 
 def workload_config(args, world):
