@@ -430,6 +430,10 @@ def main():
     barrier()
     ms_value = t0.elapsed_time(t1)
     kern_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev_pairs.items()}
+    # diagnostic: how many draws of one more sample found their subtree pre-staged
+    store.sample(u_all[0], mode=mode, want_index=False, want_priority=False)
+    scout_hits = store.info()["scout_hits"]
+    store.update_errors(err_dev[0], ALPHA, 0.01, 0, 1)
 
     # ---- e2e: public API with host buffers --------------------------------------
     np.random.seed(7 + rank)
@@ -525,7 +529,7 @@ def main():
                      "share_of_step": kern_ms["gather"] / (ms_value / K)},
         "sampler": {"mode": args.mode, "kernel": "k_sample_" + args.mode,
                     "ms_per_batch": kern_ms["sample"],
-                    "ns_per_draw": 1e6 * kern_ms["sample"] / B,
+                    "ns_per_draw": 1e6 * kern_ms["sample"] / B, "scout_prefetch_hits": scout_hits & 0xffff, "scout_not_ready": scout_hits >> 16,
                     "share_of_step": kern_ms["sample"] / (ms_value / K)},
         "clocks": clk, "prefill_s": fill_s,
         "hbm_bytes_per_rank": store.device_bytes,

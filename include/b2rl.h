@@ -179,6 +179,9 @@ typedef struct {
     double max_priority;
     int64_t napp;
     int64_t npop;
+    int32_t scout_hits; /* draws of the last exact sample whose subtree was
+                           already staged by the scout warp (diagnostic)   */
+    int32_t reserved;
 } b2rl_per_info;
 int b2rl_per_get_info(b2rl_replay *h, b2rl_per_info *out_host, void *stream);
 

@@ -157,6 +157,64 @@ def main(out_dir):
         g["ppo_%s_g_v" % tag] = t_v.grad.numpy()
         g["ppo_mean_std"] = np.array([float(mean_a), float(std_a)], dtype=np.float32)
 
+    agent_losses(out_dir)
     g["numpy_version"] = np.array(np.__version__)
     np.savez_compressed(os.path.join(out_dir, "losses.npz"), **g)
     print("wrote losses.npz with", len(g), "arrays")
+
+
+def agent_losses(out_dir):
+    """End-to-end _compute_loss of the reference's agents on a fixed batch and
+    fixed weights (fp32, CPU): pins 'fp32 losses within 1e-5'."""
+    import torch
+    import pfrl
+    from pfrl import agents, explorers, q_functions, replay_buffers
+
+    rng = np.random.RandomState(7)
+    torch.manual_seed(7)
+    B, obs, nA = 48, 10, 4
+    batch = dict(
+        state=rng.randn(B, obs).astype(np.float32), next_state=rng.randn(B, obs).astype(np.float32),
+        action=rng.randint(0, nA, size=B).astype(np.int64),
+        reward=rng.choice([-1.0, 0.0, 1.0, 0.3], size=B).astype(np.float32),
+        discount=(0.99 ** rng.randint(1, 4, size=B)).astype(np.float32),
+        is_state_terminal=(rng.rand(B) < 0.2).astype(np.float32),
+        weights=(rng.rand(B) + 0.2).astype(np.float32))
+    g = {"batch_" + k: v for k, v in batch.items()}
+    tb = {k: torch.tensor(v) for k, v in batch.items()}
+
+    def run(name, cls, qf, **kw):
+        target_init = None
+        agent = cls(qf, torch.optim.SGD(qf.parameters(), lr=0.0),
+                    replay_buffers.PrioritizedReplayBuffer(100), 0.99, explorers.Greedy(),
+                    replay_start_size=10, minibatch_size=8, **kw)
+        # make the target net differ from the online net
+        with torch.no_grad():
+            for p in agent.target_model.parameters():
+                p.add_(torch.randn_like(p) * 0.05)
+        for k, v in agent.model.state_dict().items():
+            g["%s_model_%s" % (name, k)] = v.numpy().copy()
+        for k, v in agent.target_model.state_dict().items():
+            g["%s_target_%s" % (name, k)] = v.numpy().copy()
+        for use_w in (1, 0):
+            eb = dict(tb)
+            if not use_w:
+                del eb["weights"]
+            errs = []
+            agent.model.zero_grad()
+            loss = agent._compute_loss(eb, errors_out=errs)
+            loss.backward()
+            g["%s_w%d_loss" % (name, use_w)] = loss.detach().numpy()
+            g["%s_w%d_errors" % (name, use_w)] = np.asarray(errs, dtype=np.float32)
+            g["%s_w%d_gradnorm" % (name, use_w)] = np.float32(
+                torch.sqrt(sum((p.grad ** 2).sum() for p in agent.model.parameters())))
+
+    run("dqn", agents.DQN, q_functions.FCStateQFunctionWithDiscreteAction(obs, nA, 32, 2))
+    run("ddqn", agents.DoubleDQN, q_functions.FCStateQFunctionWithDiscreteAction(obs, nA, 32, 2),
+        clip_delta=False, batch_accumulator="sum")
+    run("c51", agents.CategoricalDQN,
+        q_functions.DistributionalFCStateQFunctionWithDiscreteAction(obs, nA, 51, -10, 10, 32, 2))
+    run("rainbow", agents.CategoricalDoubleDQN,
+        q_functions.DistributionalFCStateQFunctionWithDiscreteAction(obs, nA, 21, -2, 2, 32, 2))
+    np.savez_compressed(os.path.join(out_dir, "agent_losses.npz"), **g)
+    print("wrote agent_losses.npz with", len(g), "arrays")

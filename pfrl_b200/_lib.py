@@ -100,6 +100,8 @@ class PerInfo(ctypes.Structure):
         ("max_priority", ctypes.c_double),
         ("napp", ctypes.c_int64),
         ("npop", ctypes.c_int64),
+        ("scout_hits", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 

@@ -19,6 +19,7 @@
 // is contiguous in the heap), so a draw costs one global latency, not one per
 // level.
 #include <math.h>
+#include <stdlib.h>
 
 #include "b2rl_internal.cuh"
 
@@ -46,7 +47,7 @@ struct SampleArgs {
     double *prio_user;    // optional
 };
 
-extern __shared__ double smem_d[];
+extern __shared__ __align__(128) double smem_d[];
 
 __global__ void __launch_bounds__(256, 1) k_sample_exact(SampleArgs a)
 {
@@ -233,101 +234,266 @@ __device__ __forceinline__ void spec_descend(const double *val, int &node, doubl
     }
 }
 
+// ---- TMA-style bulk copies (cp.async.bulk, SASS UBLKCP) for the 128 KB top ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_smem(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_smem(int *p, int v)
+{
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+// Three warps per launch.
+//   warp 0 (main)   walks the draws in order, exactly as the reference does.
+//   warps 1, 2 (scouts) run a couple of draws ahead on the not-yet-final
+//                   tree (alternating draws), predict which level-13 node a
+//                   future draw will pick and stage that node's lower levels
+//                   into shared memory, so that the main warp's only global
+//                   round trip per draw is usually already done when it gets
+//                   there (measured: ~99 % of the draws).
+// The prediction is only a prefetch hint: the main warp uses the staged copy
+// iff the predicted node equals the node its own exact descent reached AND no
+// draw in flight when the copy was taken could have changed that subtree
+// (release/acquire on `main_done` + "node != previous node"); otherwise it
+// fetches itself.  The arithmetic of the main warp is unchanged, so indices
+// stay bit-identical to the reference.
+// Shared memory: [top 2^14 f64][sub_own 2^(D+1)][sub_pref 2 x 2^(D+1)][out
+// staging][flags][mbarrier].  The top arrives / leaves by bulk async copy.
 template <int D>
-__global__ void __launch_bounds__(256, 1) k_sample_exact_deep(SampleArgs a)
+__global__ void __launch_bounds__(96, 1) k_sample_exact_deep(SampleArgs a)
 {
     constexpr int T = TOP_LEVELS; // shared memory holds heap levels 0..T-1
     constexpr int TOPN = 1 << T;
+    constexpr int SUBN = 2 << D;
     constexpr int PAIRS = (1 << D) - 1;       // child pairs below the chosen top node
     constexpr int NIT = (PAIRS + 31) / 32;
+    constexpr int CHUNK = 32;                 // draws per output / u staging chunk
+    constexpr int NSCOUT = 2;                 // scout warps (warp 1..NSCOUT), round-robin over draws
+    constexpr int LAG = 2;                    // scout reads the tree as of draw k-1-LAG
+    constexpr int NBUF = LAG + 1;             // staged subtrees alive at once
+    constexpr int F_READY = 0, F_NODE = 4, F_DONE = 8;
     double *top = smem_d;
-    double *sub = smem_d + TOPN;
-    const int tid = threadIdx.x;
-    {
-        const double2 *src = reinterpret_cast<const double2 *>(a.sum);
-        double2 *dst = reinterpret_cast<double2 *>(top);
-        for (int i = tid; i < TOPN / 2; i += blockDim.x) dst[i] = src[i];
+    double *sub_own = smem_d + TOPN;
+    double *sub_pref = sub_own + SUBN;                            // [NBUF][SUBN]
+    double *o_prio = sub_pref + NBUF * SUBN;                      // [CHUNK]
+    int *o_slot = reinterpret_cast<int *>(o_prio + CHUNK);        // [CHUNK]
+    int *flags = o_slot + CHUNK;  // ready_seq[NBUF] @0, pred_node[NBUF] @4, main_done @8
+    uint64_t *bar = reinterpret_cast<uint64_t *>(flags + 16);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; i++) flags[i] = -1;
+        flags[F_DONE] = 0;
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, TOPN * 8);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            bulk_g2s(top + c * (TOPN / 4), a.sum + c * (TOPN / 4), TOPN * 2, bar);
     }
     __syncthreads();
+    mbar_wait(bar, 0);
 
-    if (tid < 32) {
-        const int lane = tid;
-        const long long mask = a.nslots - 1;
-        const long long npop = a.st->npop;
-        const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
-        const uint64_t pol = policy_evict_last();
-        const double2 *sum2 = reinterpret_cast<const double2 *>(a.sum);
-        if (lane == 0) {
-            a.st->last_total = top[1];
-            a.st->last_min = a.mn[1];
-            a.st->last_n = a.n;
-        }
-        double unext = a.u[0];
-        for (int k = 0; k < a.n; k++) {
-            const double uk = unext;
-            if (k + 1 < a.n) unext = a.u[k + 1];
-            double pos = __dmul_rn(top[1], uk);
+    const long long mask = a.nslots - 1;
+    const long long npop = a.st->npop;
+    const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+    const uint64_t pol = policy_evict_last();
+    const double2 *sum2 = reinterpret_cast<const double2 *>(a.sum);
+
+    if (warp >= 1) {
+        // ------------------------------ scouts -------------------------------
+        // scout s stages draws k = 1 + s, 1 + s + NSCOUT, ...; each runs up to
+        // LAG draws ahead of the last COMPLETED draw
+        for (int k = warp; k < a.n; k += NSCOUT) {
+            const double uk = a.u[k];
+            // draws 0..k-1-LAG must be complete (their stores visible) before we read
+            while (ld_acquire_smem(&flags[F_DONE]) < k - LAG) __nanosleep(64);
+            double pos = uk * top[1]; // approximate: up to LAG draws still in flight
             int node = older;
             {
                 const double left = top[older];
-                if (!(pos < left)) {
-                    pos = __dsub_rn(pos, left);
-                    node = older ^ 1;
-                }
+                if (!(pos < left)) { pos -= left; node = older ^ 1; }
             }
-            spec_descend<T - 2>(top, node, pos, lane); // level 1 -> T-1
-            // ---- one round trip for the D levels under `node` ----------------
-            // lane-constant (q, depth, offset) per unrolled load; q = 0 is
-            // clamped to 1 and q > PAIRS cannot happen (PAIRS + 1 = 2^D)
-            double2 tmp[NIT];
+            spec_descend<T - 2>(top, node, pos, lane);
+            double *dst = sub_pref + (k % NBUF) * SUBN;
             const unsigned unode = (unsigned)node;
+            double2 tmp[NIT];
 #pragma unroll
             for (int it = 0; it < NIT; it++) {
                 int q = lane + 32 * it;
                 q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
                 const int dq = 31 - __clz(q);
-                const unsigned g = (unode << dq) + (unsigned)(q - (1 << dq));
-                tmp[it] = ld_tree_pair(sum2 + g, pol);
+                tmp[it] = ld_tree_pair(sum2 + ((unode << dq) + (unsigned)(q - (1 << dq))), pol);
             }
 #pragma unroll
             for (int it = 0; it < NIT; it++) {
                 int q = lane + 32 * it;
                 q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
-                reinterpret_cast<double2 *>(sub)[q] = tmp[it];
+                reinterpret_cast<double2 *>(dst)[q] = tmp[it];
             }
             __syncwarp();
-            int rel = 1;
-            spec_descend<D>(sub, rel, pos, lane);
-            const unsigned leafnode = (unode << D) + (unsigned)(rel - (1 << D));
-            const double prio = sub[rel];
-            // ---- re-reduce the path: siblings first, then the add chain -------
-            double sib[D + T - 1];
+            if (lane == 0) {
+                flags[F_NODE + (k % NBUF)] = node;
+                st_release_smem(&flags[F_READY + (k % NBUF)], k);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------- main --------------------------------
+        if (lane == 0) {
+            a.st->last_total = top[1];
+            a.st->last_min = a.mn[1];
+            a.st->last_n = a.n;
+        }
+        int prev_node[LAG];
 #pragma unroll
-            for (int j = 0; j < D; j++) sib[j] = sub[(rel >> j) ^ 1];
-#pragma unroll
-            for (int j = 0; j < T - 1; j++) sib[D + j] = top[(node >> j) ^ 1];
-            double v = 0.0;
-            if (lane == 0) st_tree(a.sum + leafnode, 0.0, pol);
-#pragma unroll
-            for (int j = 0; j < D; j++) {
-                v = __dadd_rn(v, sib[j]);
-                if (lane == 0) {
-                    if (j + 1 < D) {
-                        const int dp = D - j - 1; // depth of the relative parent
-                        const unsigned p = (unsigned)(rel >> (j + 1));
-                        st_tree(a.sum + ((unode << dp) + (p - (1u << dp))), v, pol);
-                    } else {
-                        top[node] = v;
+        for (int i = 0; i < LAG; i++) prev_node[i] = -1;
+        int hits = 0, late = 0;
+        for (int k0 = 0; k0 < a.n; k0 += CHUNK) {
+            const double u_lane = (k0 + lane < a.n) ? a.u[k0 + lane] : 0.0;
+            const int kend = (a.n - k0 < CHUNK) ? a.n - k0 : CHUNK;
+            for (int kk = 0; kk < kend; kk++) {
+                const int k = k0 + kk;
+                const double uk = __shfl_sync(0xffffffffu, u_lane, kk);
+                double pos = __dmul_rn(top[1], uk);
+                int node = older;
+                {
+                    const double left = top[older];
+                    if (!(pos < left)) {
+                        pos = __dsub_rn(pos, left);
+                        node = older ^ 1;
                     }
                 }
-            }
+                spec_descend<T - 2>(top, node, pos, lane); // level 1 -> T-1
+                const unsigned unode = (unsigned)node;
+                // ---- the D levels under `node`: staged by the scout, or fetched here
+                const double *sub;
+                const int ready_seq = ld_acquire_smem(&flags[F_READY + (k % NBUF)]);
+                bool staged = ready_seq == k && flags[F_NODE + (k % NBUF)] == node;
+                if (ready_seq != k) late++;
 #pragma unroll
-            for (int j = 0; j < T - 1; j++) {
-                v = __dadd_rn(v, sib[D + j]);
-                if (lane == 0) top[node >> (j + 1)] = v;
+                for (int i = 0; i < LAG; i++) staged = staged && node != prev_node[i];
+                if (staged) {
+                    sub = sub_pref + (k % NBUF) * SUBN;
+                    hits++;
+                } else {
+                    double2 tmp[NIT];
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        int q = lane + 32 * it;
+                        q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                        const int dq = 31 - __clz(q);
+                        tmp[it] =
+                            ld_tree_pair(sum2 + ((unode << dq) + (unsigned)(q - (1 << dq))), pol);
+                    }
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        int q = lane + 32 * it;
+                        q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                        reinterpret_cast<double2 *>(sub_own)[q] = tmp[it];
+                    }
+                    __syncwarp();
+                    sub = sub_own;
+                }
+                int rel = 1;
+                spec_descend<D>(sub, rel, pos, lane);
+                const unsigned leafnode = (unode << D) + (unsigned)(rel - (1 << D));
+                const double prio = sub[rel];
+                // ---- re-reduce the path: siblings first, then the add chain ---
+                double sib[D + T - 1];
+#pragma unroll
+                for (int j = 0; j < D; j++) sib[j] = sub[(rel >> j) ^ 1];
+#pragma unroll
+                for (int j = 0; j < T - 1; j++) sib[D + j] = top[(node >> j) ^ 1];
+                double v = 0.0;
+                if (lane == 0) st_tree(a.sum + leafnode, 0.0, pol);
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    v = __dadd_rn(v, sib[j]);
+                    if (lane == 0) {
+                        if (j + 1 < D) {
+                            const int dp = D - j - 1; // depth of the relative parent
+                            const unsigned p = (unsigned)(rel >> (j + 1));
+                            st_tree(a.sum + ((unode << dp) + (p - (1u << dp))), v, pol);
+                        } else {
+                            top[node] = v;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < T - 1; j++) {
+                    v = __dadd_rn(v, sib[D + j]);
+                    if (lane == 0) top[node >> (j + 1)] = v;
+                }
+                if (lane == 0) {
+                    o_slot[kk] = (int)(leafnode - (unsigned)a.nslots);
+                    o_prio[kk] = prio;
+                    // publish "draws 0..k are complete" (global + shared stores above)
+                    st_release_smem(&flags[F_DONE], k + 1);
+                }
+#pragma unroll
+                for (int i = LAG - 1; i > 0; i--) prev_node[i] = prev_node[i - 1];
+                prev_node[0] = node;
+                __syncwarp();
             }
-            if (lane == 0) {
-                const long long slot = (long long)leafnode - a.nslots;
+            if (lane < kend) {
+                const int k = k0 + lane;
+                const long long slot = o_slot[lane];
+                const double prio = o_prio[lane];
                 a.slots_out[k] = (int32_t)slot;
                 a.prio_out[k] = prio;
                 if (a.index_out) a.index_out[k] = (slot - npop) & mask;
@@ -335,21 +501,26 @@ __global__ void __launch_bounds__(256, 1) k_sample_exact_deep(SampleArgs a)
             }
             __syncwarp();
         }
+        if (lane == 0) a.st->pad = hits | (late << 16); // scout diagnostics: hits, not-ready
     }
     __syncthreads();
-    {
-        double2 *dst = reinterpret_cast<double2 *>(a.sum);
-        const double2 *src = reinterpret_cast<const double2 *>(top);
-        for (int i = tid; i < TOPN / 2; i += blockDim.x)
-            if (i > 0) dst[i] = src[i];
-        if (tid == 0) a.sum[1] = top[1];
+    // publish the shared-memory levels (zeroed state) back to HBM: bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            bulk_s2g(a.sum + c * (TOPN / 4), top + c * (TOPN / 4), TOPN * 2);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
 template <int D>
 static cudaError_t launch_deep(const SampleArgs &a, cudaStream_t s)
 {
-    const size_t smem = sizeof(double) * ((size_t(1) << TOP_LEVELS) + (size_t(2) << D));
+    const size_t smem = sizeof(double) * ((size_t(1) << TOP_LEVELS) + 4 * (size_t(2) << D) + 32) +
+                        sizeof(int) * (32 + 16) + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_sample_exact_deep<D>,
@@ -358,7 +529,7 @@ static cudaError_t launch_deep(const SampleArgs &a, cudaStream_t s)
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_sample_exact_deep<D><<<1, 256, smem, s>>>(a);
+    k_sample_exact_deep<D><<<1, 96, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -708,6 +879,8 @@ extern "C" int b2rl_per_get_info(b2rl_replay *h, b2rl_per_info *out, void *strea
     out->max_priority = st.max_priority;
     out->napp = st.napp;
     out->npop = st.npop;
+    out->scout_hits = st.pad;
+    out->reserved = 0;
     return B2RL_OK;
 }
 

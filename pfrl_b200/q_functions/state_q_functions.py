@@ -1,5 +1,6 @@
 """Q-function heads for vector observations
 (pfrl/q_functions/state_q_functions.py)."""
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -57,7 +58,8 @@ class DistributionalFCStateQFunctionWithDiscreteAction(
                  n_hidden_layers, nonlinearity=F.relu, last_wscale=1.0):
         assert n_atoms >= 2
         assert v_min < v_max
-        z_values = torch.linspace(v_min, v_max, n_atoms, dtype=torch.float32)
+        # numpy linspace (fp64 then cast), as in the reference (state_q_functions.py:128)
+        z_values = torch.from_numpy(np.linspace(v_min, v_max, num=n_atoms, dtype=np.float32))
 
         class _Head(nn.Module):
             def forward(self, h):

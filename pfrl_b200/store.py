@@ -161,7 +161,7 @@ class DeviceReplayStore:
         out = _lib.PerInfo()
         _lib.check(self.L.b2rl_per_get_info(self.h, ctypes.byref(out), _stream()))
         return dict(total=out.total, min=out.min, max_priority=out.max_priority,
-                    napp=out.napp, npop=out.npop)
+                    napp=out.napp, npop=out.npop, scout_hits=out.scout_hits)
 
     def read_priorities(self, first=0, n=None):
         if n is None:
