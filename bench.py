@@ -193,7 +193,8 @@ def make_rainbow_agent(buf, dev_index, batch, grad_sync=None):
     torch.manual_seed(0)
     q = q_functions.DistributionalDuelingDQN(18, 51, -10, 10)
     pnn.to_factorized_noisy(q, sigma_scale=0.5)
-    opt = torch.optim.Adam(q.parameters(), 6.25e-5, eps=1.5e-4)
+    q.to(torch.device('cuda', dev_index))
+    opt = torch.optim.Adam(q.parameters(), 6.25e-5, eps=1.5e-4, fused=True)
     agent = agents.CategoricalDoubleDQN(
         q, opt, buf, gpu=dev_index, gamma=GAMMA, explorer=explorers.Greedy(),
         minibatch_size=batch, replay_start_size=batch, target_update_interval=32000,

@@ -295,6 +295,15 @@ int b2rl_ppo_loss(const float *log_prob, const float *entropy,
                   float entropy_coef, float *g_log_prob, float *g_entropy,
                   float *g_v_pred, double *scratch, float *losses, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Dense contraction kept in exact fp32: first Nature-DQN convolution,
+ * x[N,4,84,84] * w[32,4,8,8] (stride 4) + bias -> out[N,32,20,20].
+ * Replaces the cuDNN call behind nn.Conv2d(4, 32, 8, stride=4)
+ * (pfrl/nn/atari_cnn.py:30-36, pfrl/q_functions/dueling_dqn.py:34-40,91-97)
+ * in the forward direction; bias may be NULL. */
+int b2rl_conv_nature1_fwd(const float *x, const float *w, const float *bias,
+                          int32_t n_images, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libb2rl.so")
-SOURCES = ["replay.cu", "sampler.cu", "gather.cu", "losses.cu", "ppo.cu"]
+SOURCES = ["replay.cu", "sampler.cu", "gather.cu", "losses.cu", "ppo.cu", "conv.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -141,6 +141,7 @@ SIGNATURES = {
     "b2rl_quantile_huber_bwd": (_int, [_vp] * 5 + [_i32, _i32, _i32, _int, _vp, _vp]),
     "b2rl_gae": (_int, [_vp] * 6 + [_i32, _i32, _dbl, _dbl] + [_vp] * 5),
     "b2rl_ppo_loss": (_int, [_vp] * 8 + [_i32] + [ctypes.c_float] * 4 + [_vp] * 6),
+    "b2rl_conv_nature1_fwd": (_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
 }
 
 _lib = None

@@ -4,6 +4,7 @@ served by cuDNN / cuBLAS."""
 import torch.nn as nn
 import torch.nn.functional as F
 
+from pfrl_b200.nn.fast_conv import NatureConv1
 from pfrl_b200.initializers import constant_bias_initializer, init_chainer_default
 
 
@@ -30,7 +31,7 @@ class LargeAtariCNN(_AtariCNN):
     def __init__(self, n_input_channels=4, n_output_channels=512, activation=F.relu, bias=0.1):
         self.n_input_channels = n_input_channels
         super().__init__(
-            [nn.Conv2d(n_input_channels, 32, 8, stride=4), nn.Conv2d(32, 64, 4, stride=2),
+            [NatureConv1(n_input_channels), nn.Conv2d(32, 64, 4, stride=2),
              nn.Conv2d(64, 64, 3, stride=1)], 3136, n_output_channels, activation, bias)
 
 

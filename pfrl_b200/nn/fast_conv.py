@@ -1,0 +1,54 @@
+"""nn.Conv2d with a hand-written fp32 forward for the first Nature-DQN layer.
+
+``NatureConv1`` IS an ``nn.Conv2d(4, 32, 8, stride=4)`` (same parameters,
+same state_dict keys).  On CUDA, for contiguous fp32 [N, 4, 84, 84] inputs
+that do not require grad (observations), the forward runs
+``b2rl_conv_nature1_fwd`` (csrc/conv.cu: exact fp32 FFMA accumulation, several
+times faster than cuDNN's TF32-off path); weight / bias gradients come from
+``aten::convolution_backward``.  Everything else falls through to cuDNN.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from pfrl_b200 import _lib
+
+
+class _Conv1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        L = _lib.load()
+        n = x.shape[0]
+        out = torch.empty((n, 32, 20, 20), dtype=torch.float32, device=x.device)
+        w = weight.detach().contiguous()
+        b = None if bias is None else bias.detach().contiguous()
+        _lib.check(L.b2rl_conv_nature1_fwd(
+            ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+            None if b is None else ctypes.c_void_p(b.data_ptr()), n,
+            ctypes.c_void_p(out.data_ptr()),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight = ctx.saved_tensors
+        _, gw, gb = torch.ops.aten.convolution_backward(
+            grad_out.contiguous(), x, weight, [32] if ctx.has_bias else None, [4, 4], [0, 0],
+            [1, 1], False, [0, 0], 1, [False, True, ctx.has_bias])
+        return None, gw, gb if ctx.has_bias else None
+
+
+class NatureConv1(nn.Conv2d):
+    def __init__(self, n_input_channels=4):
+        super().__init__(n_input_channels, 32, 8, stride=4)
+
+    def forward(self, x):
+        if (x.is_cuda and x.dtype == torch.float32 and x.ndim == 4
+                and tuple(x.shape[1:]) == (4, 84, 84) and self.in_channels == 4
+                and not x.requires_grad and x.is_contiguous()
+                and self.weight.dtype == torch.float32):
+            return _Conv1Fn.apply(x, self.weight, self.bias)
+        return super().forward(x)

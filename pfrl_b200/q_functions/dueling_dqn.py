@@ -7,13 +7,14 @@ import torch.nn.functional as F
 
 from pfrl_b200 import action_value
 from pfrl_b200.initializers import constant_bias_initializer, init_chainer_default
+from pfrl_b200.nn.fast_conv import NatureConv1
 from pfrl_b200.nn.mlp import MLP
 from pfrl_b200.q_function import StateQFunction
 
 
 def _nature_convs(n_input_channels):
     return nn.ModuleList([
-        nn.Conv2d(n_input_channels, 32, 8, stride=4),
+        NatureConv1(n_input_channels),
         nn.Conv2d(32, 64, 4, stride=2),
         nn.Conv2d(64, 64, 3, stride=1),
     ])

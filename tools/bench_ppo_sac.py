@@ -1,0 +1,96 @@
+"""Secondary workloads (BASELINE configs[3], configs[4]) on one GPU: PPO on a
+synthetic Humanoid-shaped env (obs 376, act 17, 256 envs, lambda .95) and SAC
+(obs 17, act 6, 1M replay, batch 1024).  Prints one JSON line per workload.
+Dev / evidence tool: python tools/bench_ppo_sac.py  (GPU box)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+from torch import distributions, nn
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pfrl_b200 import agents, nn as pnn, policies  # noqa: E402
+from pfrl_b200.envs import SyntheticContinuousVectorEnv  # noqa: E402
+from pfrl_b200.replay_buffers import ReplayBuffer  # noqa: E402
+from pfrl_b200.utils.phi import Identity  # noqa: E402
+
+
+def loop(agent, env, steps):
+    obs = env.reset()
+    for _ in range(steps):
+        a = agent.batch_act(obs)
+        obs, r, d, info = env.step(a)
+        agent.batch_observe(obs, r, d, np.zeros(env.num_envs, dtype=bool))
+        obs = env.reset(np.logical_not(d))
+
+
+def timed(agent, env, steps, warm):
+    loop(agent, env, warm)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loop(agent, env, steps)
+    torch.cuda.synchronize()
+    return time.perf_counter() - t0
+
+
+def ppo():
+    obs_dim, act_dim, E, T = 376, 17, 256, 8
+    model = nn.Sequential(
+        pnn.Branched(
+            nn.Sequential(nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh(),
+                          nn.Linear(64, act_dim),
+                          policies.GaussianHeadWithStateIndependentCovariance(
+                              action_size=act_dim, var_type="diagonal",
+                              var_func=lambda x: torch.exp(2 * x), var_param_init=0)),
+            nn.Sequential(nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh(),
+                          nn.Linear(64, 1))))
+    agent = agents.PPO(model, torch.optim.Adam(model.parameters(), lr=3e-4, eps=1e-5),
+                       obs_normalizer=pnn.EmpiricalNormalization(obs_dim, clip_threshold=5),
+                       gpu=0, gamma=0.995, lambd=0.95, update_interval=E * T, minibatch_size=64,
+                       epochs=10, clip_eps=0.2, clip_eps_vf=None, entropy_coef=0.0)
+    env = SyntheticContinuousVectorEnv(E, obs_dim, act_dim, device="cuda", seed=0)
+    steps = 4 * T
+    dt = timed(agent, env, steps, T)
+    print(json.dumps({"workload": "PPO configs[3]: obs 376 act 17, 256 envs, T=8 (2048/update), "
+                      "minibatch 64 x 10 epochs", "env_steps_per_sec": steps * E / dt,
+                      "updates": agent.n_updates, "seconds": dt}))
+
+
+def sac():
+    obs_dim, act_dim, E = 17, 6, 16
+
+    def squashed(x):
+        mean, log_scale = torch.chunk(x, 2, dim=1)
+        base = distributions.Independent(
+            distributions.Normal(mean, torch.exp(torch.clamp(log_scale, -20, 2))), 1)
+        return distributions.transformed_distribution.TransformedDistribution(
+            base, [distributions.transforms.TanhTransform(cache_size=1)])
+
+    policy = nn.Sequential(nn.Linear(obs_dim, 256), nn.ReLU(), nn.Linear(256, 256), nn.ReLU(),
+                           nn.Linear(256, 2 * act_dim), pnn.Lambda(squashed))
+
+    def qf():
+        return nn.Sequential(pnn.ConcatObsAndAction(), nn.Linear(obs_dim + act_dim, 256), nn.ReLU(),
+                             nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 1))
+
+    q1, q2 = qf(), qf()
+    agent = agents.SoftActorCritic(
+        policy, q1, q2, torch.optim.Adam(policy.parameters(), lr=3e-4),
+        torch.optim.Adam(q1.parameters(), lr=3e-4), torch.optim.Adam(q2.parameters(), lr=3e-4),
+        ReplayBuffer(10 ** 6), gamma=0.99, gpu=0, replay_start_size=2048, minibatch_size=1024,
+        entropy_target=-act_dim, temperature_optimizer_lr=3e-4, phi=Identity())
+    env = SyntheticContinuousVectorEnv(E, obs_dim, act_dim, device="cuda", seed=1)
+    loop(agent, env, 2048 // E + 4)
+    steps = 40
+    dt = timed(agent, env, steps, 4)
+    print(json.dumps({"workload": "SAC configs[4]: obs 17 act 6, 1M uniform replay, batch 1024, "
+                      "update every env step", "env_steps_per_sec": steps * E / dt,
+                      "updates_per_sec": steps * E / dt, "seconds": dt}))
+
+
+if __name__ == "__main__":
+    ppo()
+    sac()

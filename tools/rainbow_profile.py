@@ -1,7 +1,7 @@
 """Where does a Rainbow training step spend its time?  (dev tool, GPU box)"""
 import sys, time
 import numpy as np, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench
 from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
 from pfrl_b200.envs import SyntheticAtariVectorEnv
