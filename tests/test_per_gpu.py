@@ -184,3 +184,33 @@ def test_parallel_sampler_matches_frozen_descent():
         assert gi[k] == oi[0]
     store.update_priorities(gp)
     store.close()
+
+
+def test_parallel_sampler_follows_the_priority_distribution():
+    """Throughput mode (with replacement, frozen tree): hit frequencies must be
+    proportional to the priorities (the statistical contract of the
+    reference's own tests/collections_tests/test_prioritized.py:9-51)."""
+    cap = 4096
+    store = make_store(cap, max_batch=4096)
+    rng = np.random.RandomState(9)
+    pri = rng.rand(cap) ** 3 + 0.01
+    z = np.zeros((cap, 1), dtype=np.int32)
+    store.append(z, z, np.zeros(cap, np.int64), np.zeros((cap, 1)), np.ones(cap, np.uint8),
+                 np.zeros(cap, np.uint8), priority=pri)
+    counts = np.zeros(cap)
+    rounds = 200
+    for _ in range(rounds):
+        idx, p = store.sample(rng.random_sample(4096), mode=1)
+        counts += np.bincount(idx.cpu().numpy(), minlength=cap)
+        store.update_priorities(p)  # unchanged priorities
+    expected = pri / pri.sum() * rounds * 4096
+    # correlation with the target law and a chi-square in 64 buckets
+    assert np.corrcoef(counts, expected)[0, 1] > 0.99
+    order = np.argsort(pri)
+    cb = counts[order].reshape(64, -1).sum(1)
+    eb = expected[order].reshape(64, -1).sum(1)
+    chi2 = ((cb - eb) ** 2 / eb).sum()
+    assert chi2 < 120, chi2  # 63 dof: P(chi2 > 120) ~ 2e-5
+    leaves = store.read_priorities()
+    assert leaves.tobytes() == pri.tobytes()  # the tree is untouched by parallel sampling
+    store.close()
