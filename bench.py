@@ -83,7 +83,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -417,12 +417,12 @@ def main():
             ev_pairs["update"].append((e[4], e[5]))
         return out, w
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # samples SM clock / throttle reasons through all timed regions
     for i in range(W):
         step_value(i, False)
     barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     t0, t1 = ev(), ev()
     t0.record()
     for i in range(W, W + K):
@@ -461,7 +461,6 @@ def main():
     t3.record()
     barrier()
     ms_e2e = t2.elapsed_time(t3)
-    clk = clocks.stop() if rank == 0 else None
 
     # ---- Rainbow training loop on the same shard ----------------------------------
     rb = None
@@ -487,6 +486,8 @@ def main():
             barrier()
             res[tag] = (a.elapsed_time(b), agent.optim_t - n0)
         rb = (res, vec_steps)
+
+    clk = clocks.stop() if rank == 0 else None
 
     # ---- max over ranks ---------------------------------------------------------
     tm = torch.tensor([ms_value, ms_e2e] + ([rb[0]["value"][0], rb[0]["e2e"][0]] if rb else []),

@@ -1,5 +1,5 @@
 from pfrl_b200.agents import dqn
-from pfrl_b200.utils.contexts import evaluating
+from pfrl_b200.utils.modes import evaluating
 
 
 class DoubleDQN(dqn.DQN):

@@ -30,7 +30,7 @@ from pfrl_b200.agents.dqn import _DeviceRing
 from pfrl_b200.agents.soft_actor_critic import mode_of_distribution
 from pfrl_b200.ops import ppo as fused
 from pfrl_b200.utils.batch_states import batch_states
-from pfrl_b200.utils.contexts import evaluating
+from pfrl_b200.utils.modes import evaluating
 
 
 def _elementwise_clip(x, x_min, x_max):

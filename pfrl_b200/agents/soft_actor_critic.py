@@ -20,7 +20,7 @@ from pfrl_b200.agents.dqn import _DeviceRing
 from pfrl_b200.replay_buffer import ReplayUpdater, batch_experiences
 from pfrl_b200.utils import clip_l2_grad_norm_
 from pfrl_b200.utils.batch_states import batch_states
-from pfrl_b200.utils.contexts import evaluating
+from pfrl_b200.utils.modes import evaluating
 from pfrl_b200.utils.copy_param import synchronize_parameters
 
 

@@ -1,42 +1,50 @@
-from abc import ABCMeta, abstractmethod
+"""Environment interfaces the training loops rely on (reference: pfrl/env.py)."""
+import abc
 
 
-class Env(object, metaclass=ABCMeta):
-    """Single environment (pfrl/env.py:4-20)."""
+class Env(abc.ABC):
+    """One environment: ``reset() -> obs``, ``step(a) -> (obs, r, done, info)``."""
 
-    @abstractmethod
-    def step(self, action):
-        raise NotImplementedError()
-
-    @abstractmethod
+    @abc.abstractmethod
     def reset(self):
-        raise NotImplementedError()
+        ...
 
-    @abstractmethod
-    def close(self):
-        raise NotImplementedError()
-
-
-class VectorEnv(object, metaclass=ABCMeta):
-    """Batch of environments stepped together (pfrl/env.py:23-55):
-    ``step(actions) -> (obss, rewards, dones, infos)``, ``reset(mask)`` resets
-    the environments whose mask entry is False (all if mask is None)."""
-
-    @abstractmethod
+    @abc.abstractmethod
     def step(self, action):
-        raise NotImplementedError()
+        ...
 
-    @abstractmethod
-    def reset(self, mask):
-        raise NotImplementedError()
-
-    @abstractmethod
-    def seed(self, seeds):
-        raise NotImplementedError()
-
-    @abstractmethod
+    @abc.abstractmethod
     def close(self):
-        raise NotImplementedError()
+        ...
+
+
+class VectorEnv(abc.ABC):
+    """``num_envs`` environments stepped in lock-step.
+
+    ``step(actions)`` returns ``(observations, rewards, dones, infos)``, one
+    entry per environment.  ``reset(mask)`` restarts the environments whose
+    mask entry is False (all of them for ``mask=None``) and returns the current
+    observation of every environment.  ``infos[i].get("needs_reset")`` asks the
+    training loop to reset environment i although it is not terminal.
+    """
+
+    num_envs = None
+
+    @abc.abstractmethod
+    def reset(self, mask=None):
+        ...
+
+    @abc.abstractmethod
+    def step(self, actions):
+        ...
+
+    @abc.abstractmethod
+    def seed(self, seeds):
+        ...
+
+    @abc.abstractmethod
+    def close(self):
+        ...
 
     @property
     def unwrapped(self):

@@ -69,3 +69,13 @@ class LinearDecayEpsilonGreedy(explorer.Explorer):
 
     def __repr__(self):
         return "LinearDecayEpsilonGreedy(epsilon={})".format(self.epsilon)
+
+
+class Greedy(explorer.Explorer):
+    """Always the greedy action: no exploration (pfrl/explorers/greedy.py)."""
+
+    def select_action(self, t, greedy_action_func, action_value=None):
+        return greedy_action_func()
+
+    def __repr__(self):
+        return "Greedy()"

@@ -1,8 +1,6 @@
 from pfrl_b200.nn.atari_cnn import LargeAtariCNN, SmallAtariCNN  # NOQA
 from pfrl_b200.nn.empirical_normalization import EmpiricalNormalization  # NOQA
-from pfrl_b200.nn.lmbda import Lambda  # NOQA
 from pfrl_b200.nn.mlp import MLP  # NOQA
 from pfrl_b200.nn.noisy_chain import to_factorized_noisy  # NOQA
 from pfrl_b200.nn.noisy_linear import FactorizedNoisyLinear  # NOQA
-from pfrl_b200.nn.branched import Branched  # NOQA
-from pfrl_b200.nn.concat_obs_and_action import ConcatObsAndAction  # NOQA
+from pfrl_b200.nn.containers import Branched, ConcatObsAndAction, Lambda  # NOQA

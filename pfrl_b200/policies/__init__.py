@@ -1,6 +1,6 @@
-from pfrl_b200.policies.gaussian_policy import (  # NOQA
+from pfrl_b200.policies.heads import (  # NOQA
     GaussianHeadWithDiagonalCovariance,
     GaussianHeadWithFixedCovariance,
     GaussianHeadWithStateIndependentCovariance,
+    SoftmaxCategoricalHead,
 )
-from pfrl_b200.policies.softmax_policy import SoftmaxCategoricalHead  # NOQA

@@ -1,8 +1,19 @@
-"""Gaussian policy heads (pfrl/policies/gaussian_policy.py)."""
+"""Policy heads: map network outputs to torch.distributions objects.
+
+Same classes as the reference's pfrl/policies/ (softmax_policy.py:5-7,
+gaussian_policy.py:6-96), kept in one module.
+"""
 import numpy as np
 import torch
 from torch import nn
 
+
+class SoftmaxCategoricalHead(nn.Module):
+    """Unnormalised log-probabilities -> ``Categorical`` over discrete actions."""
+
+    def forward(self, logits):
+        dist = torch.distributions.Categorical(logits=logits)
+        return dist
 
 class GaussianHeadWithStateIndependentCovariance(nn.Module):
     """mean -> Independent(Normal(mean, sqrt(f(var_param)))) with a learned,

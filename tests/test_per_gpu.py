@@ -214,3 +214,21 @@ def test_parallel_sampler_follows_the_priority_distribution():
     leaves = store.read_priorities()
     assert leaves.tobytes() == pri.tobytes()  # the tree is untouched by parallel sampling
     store.close()
+
+
+def test_duplicate_slots_last_priority_wins():
+    """With replacement (parallel mode) the same leaf can be drawn twice; the
+    reference's set_last_priority writes in order, so the LAST value sticks
+    (collections/prioritized.py:111-114) and max_priority sees every value."""
+    store = make_store(8)
+    z = np.zeros((4, 1), dtype=np.int32)
+    store.append(z, z, np.zeros(4, np.int64), np.zeros((4, 1)), np.ones(4, np.uint8),
+                 np.zeros(4, np.uint8), priority=np.array([1.0, 1.0, 1.0, 1.0]))
+    idx, _ = store.sample(np.array([0.3, 0.3, 0.3, 0.9]), mode=1)  # three draws hit leaf 1
+    idx = idx.cpu().numpy()
+    assert list(idx) == [1, 1, 1, 3]
+    store.update_priorities(np.array([5.0, 7.0, 2.0, 3.0]))
+    assert list(store.read_priorities()) == [1.0, 2.0, 1.0, 3.0]
+    info = store.info()
+    assert info["max_priority"] == 7.0 and info["total"] == 7.0 and info["min"] == 1.0
+    store.close()
