@@ -167,3 +167,52 @@ def test_sac_on_device_env():
     stats = dict(agent.get_statistics())
     assert stats["n_updates"] > 300 and np.isfinite(stats["average_q1"])
     assert len(agent.replay_buffer) == 8 * 60
+
+
+def test_iqn_on_device_replay_and_fused_loss():
+    """IQN: fused quantile-Huber kernel == torch formulation on the same taus,
+    and a short training run on the device PER."""
+    from pfrl_b200 import agents, explorers
+    from pfrl_b200.agents import iqn
+    from pfrl_b200.envs import SyntheticContinuousVectorEnv
+    from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
+    from pfrl_b200.utils import set_random_seed
+    from pfrl_b200.utils.phi import Identity
+
+    set_random_seed(0)
+    obs_dim, n_actions, hidden = 12, 4, 32
+    q = iqn.ImplicitQuantileQFunction(
+        psi=nn.Sequential(nn.Linear(obs_dim, hidden), nn.ReLU()),
+        phi=nn.Sequential(iqn.CosineBasisLinear(16, hidden), nn.ReLU()),
+        f=nn.Linear(hidden, n_actions))
+    agent = agents.IQN(
+        q, torch.optim.Adam(q.parameters(), lr=1e-3), PrioritizedReplayBuffer(5000, num_steps=2),
+        0.99, explorers.ConstantEpsilonGreedy(0.2, lambda: np.random.randint(n_actions)), gpu=0,
+        replay_start_size=64, minibatch_size=32, target_update_interval=50, phi=Identity(),
+        quantile_thresholds_N=8, quantile_thresholds_N_prime=8, quantile_thresholds_K=4)
+    # loss equivalence with identical taus
+    B = 16
+    y = torch.randn(B, 8, device="cuda", requires_grad=True)
+    t = torch.randn(B, 8, device="cuda")
+    taus = torch.rand(B, 8, device="cuda")
+    w = torch.rand(B, device="cuda") + 0.1
+    from pfrl_b200.ops.losses import quantile_huber_loss
+
+    loss_f, err_f = quantile_huber_loss(y, t, taus, w, mean=True)
+    elt = iqn.compute_eltwise_huber_quantile_loss(y, t, taus)
+    loss_t = iqn.compute_weighted_value_loss(elt, w, "mean")
+    torch.testing.assert_close(loss_f, loss_t, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(err_f, elt.detach().mean((1, 2)), rtol=1e-5, atol=1e-6)
+    g_f, = torch.autograd.grad(loss_f, y)
+    g_t, = torch.autograd.grad(loss_t, y)
+    torch.testing.assert_close(g_f, g_t, rtol=1e-4, atol=1e-7)
+    # short run
+    env = SyntheticContinuousVectorEnv(4, obs_dim, 1, device="cuda", seed=2, mean_episode_len=25)
+    obs = env.reset()
+    for _ in range(60):
+        a = agent.batch_act(obs)
+        obs, r, d, info = env.step(a)
+        agent.batch_observe(obs, r, d, np.zeros(4, dtype=bool))
+        obs = env.reset(np.logical_not(d))
+    stats = dict(agent.get_statistics())
+    assert stats["n_updates"] > 100 and np.isfinite(stats["average_loss"])
