@@ -135,6 +135,7 @@ struct FixArgs {
     long long lo[4], hi[4]; // node ranges (inclusive) at the level ABOVE which we start
     int nranges;
     int start_level; // level of lo/hi; parents at start_level-1 are recomputed first
+    int levels;      // leaves live at heap level `levels`
     long long bump_n; // counters: napp += bump_n; npop = max(npop, napp - capacity)
     long long capacity;
 };
@@ -145,7 +146,10 @@ __global__ void __launch_bounds__(1024) k_tree_fix_small(FixArgs a)
 {
     long long lo[4], hi[4];
     for (int r = 0; r < a.nranges; r++) { lo[r] = a.lo[r]; hi[r] = a.hi[r]; }
-    for (int level = a.start_level; level > 0; level--) {
+    // narrow ranges, level by level (global round trip + barrier each) ...
+    const int topl = a.levels < 10 ? a.levels : 10;
+    int level = a.start_level;
+    for (; level > topl; level--) {
         for (int r = 0; r < a.nranges; r++) {
             lo[r] >>= 1;
             hi[r] >>= 1;
@@ -155,6 +159,31 @@ __global__ void __launch_bounds__(1024) k_tree_fix_small(FixArgs a)
             }
         }
         __syncthreads();
+    }
+    // ... then the top `topl` levels (<= 1023 nodes) entirely in shared memory:
+    // nodes are pure functions of their children, so recomputing all of them
+    // from level `topl` is exact and saves ten global round trips
+    if (a.nranges > 0) {
+        __shared__ double s_sum[2048], s_min[2048];
+        const int base = 1 << topl;
+        for (int i = threadIdx.x; i < base; i += blockDim.x) {
+            s_sum[base + i] = a.sum[base + i];
+            s_min[base + i] = a.mn[base + i];
+        }
+        __syncthreads();
+        for (int lv = topl - 1; lv >= 0; lv--) {
+            const int w = 1 << lv;
+            for (int i = threadIdx.x; i < w; i += blockDim.x) {
+                const int node = w + i;
+                s_sum[node] = s_sum[2 * node] + s_sum[2 * node + 1];
+                s_min[node] = fmin(s_min[2 * node], s_min[2 * node + 1]);
+            }
+            __syncthreads();
+        }
+        for (int i = 1 + threadIdx.x; i < base; i += blockDim.x) {
+            a.sum[i] = s_sum[i];
+            a.mn[i] = s_min[i];
+        }
     }
     if (threadIdx.x == 0 && a.bump_n > 0) {
         long long napp = a.st->napp + a.bump_n;
@@ -372,6 +401,7 @@ int b2rl_launch_tree_fix(b2rl_replay *h, int nranges, long long *lo, long long *
     a.nranges = nranges;
     for (int r = 0; r < nranges; r++) { a.lo[r] = lo[r]; a.hi[r] = hi[r]; }
     a.start_level = nranges ? level : 0;
+    a.levels = h->levels;
     a.bump_n = bump_n;
     a.capacity = h->cfg.capacity;
     k_tree_fix_small<<<1, 1024, 0, s>>>(a);

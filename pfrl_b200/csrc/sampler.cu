@@ -757,22 +757,65 @@ __global__ void __launch_bounds__(1024) k_update(UpdateArgs a)
         }
     }
     __syncthreads();
-    for (int lv = a.levels - 1; lv >= 0; lv--) {
-        const long long width = 1ll << lv;
-        if (width <= a.n) {
-            for (long long node = width + tid; node < 2 * width; node += nt) {
-                a.sum[node] = a.sum[2 * node] + a.sum[2 * node + 1];
-                a.mn[node] = fmin(a.mn[2 * node], a.mn[2 * node + 1]);
+    // lower levels: one node per updated leaf and level, block barrier per level.
+    // The leaf index stays in a register (n <= 4 * blockDim), so a level costs
+    // one round trip for the four child loads instead of two dependent ones.
+    const int topl = a.levels < 10 ? a.levels : 10; // levels < topl are redone in shared memory
+    if (a.n <= 4 * nt) {
+        long long leaf[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = tid + j * nt;
+            leaf[j] = k < a.n ? a.nslots + a.slots[k] : -1;
+        }
+        for (int lv = a.levels - 1; lv >= topl; lv--) {
+            const int sh = a.levels - lv;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (leaf[j] < 0) continue;
+                const long long node = leaf[j] >> sh;
+                const double2 sc = *reinterpret_cast<const double2 *>(a.sum + 2 * node);
+                const double2 mc = *reinterpret_cast<const double2 *>(a.mn + 2 * node);
+                a.sum[node] = sc.x + sc.y;
+                a.mn[node] = fmin(mc.x, mc.y);
             }
-        } else {
+            __syncthreads();
+        }
+    } else {
+        for (int lv = a.levels - 1; lv >= topl; lv--) {
             const int sh = a.levels - lv;
             for (int k = tid; k < a.n; k += nt) {
                 const long long node = (a.nslots + a.slots[k]) >> sh;
                 a.sum[node] = a.sum[2 * node] + a.sum[2 * node + 1];
                 a.mn[node] = fmin(a.mn[2 * node], a.mn[2 * node + 1]);
             }
+            __syncthreads();
+        }
+    }
+    // top `topl` levels (<= 1023 nodes per tree): every node is a pure function
+    // of its children, so recompute them all from level `topl` in shared memory
+    // (cheap barriers) instead of ten more global round trips
+    {
+        __shared__ double s_sum[2048], s_min[2048];
+        const int base = 1 << topl;
+        for (int i = tid; i < base; i += nt) {
+            s_sum[base + i] = a.sum[base + i];
+            s_min[base + i] = a.mn[base + i];
         }
         __syncthreads();
+        for (int lv = topl - 1; lv >= 0; lv--) {
+            const int w = 1 << lv;
+            for (int i = tid; i < w; i += nt) {
+                const int node = w + i;
+                s_sum[node] = s_sum[2 * node] + s_sum[2 * node + 1];
+                s_min[node] = fmin(s_min[2 * node], s_min[2 * node + 1]);
+            }
+            __syncthreads();
+        }
+        for (int i = 1 + tid; i < base; i += nt) {
+            a.sum[i] = s_sum[i];
+            a.mn[i] = s_min[i];
+        }
     }
     for (int k = tid; k < a.n; k += nt) a.winner[a.slots[k]] = -1;
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
