@@ -168,12 +168,9 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
         predict_q2 = torch.flatten(self.q_func2((state, actions)))
         loss1 = 0.5 * F.mse_loss(target_q, predict_q1)
         loss2 = 0.5 * F.mse_loss(target_q, predict_q2)
-        self.q1_record.extend(predict_q1)
-        self.q2_record.extend(predict_q2)
-        self.q_func1_loss_record.append(loss1.detach())
-        self.q_func2_loss_record.append(loss2.detach())
         self._step(self.q_func1_optimizer, self.q_func1, loss1)
         self._step(self.q_func2_optimizer, self.q_func2, loss2)
+        return predict_q1.detach(), predict_q2.detach(), loss1.detach(), loss2.detach()
 
     def update_temperature(self, log_prob):
         assert not log_prob.requires_grad
@@ -191,20 +188,31 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
         assert q.shape == entropy_term.shape
         loss = torch.mean(entropy_term - q)
         self._step(self.policy_optimizer, self.policy, loss)
-        self.n_policy_updates += 1
         if self.entropy_target is not None:
             self.update_temperature(log_prob.detach())
         with torch.no_grad():
             try:
-                self.entropy_record.extend(action_distrib.entropy())
+                return action_distrib.entropy().detach()
             except NotImplementedError:
-                self.entropy_record.extend(-log_prob)
+                return -log_prob.detach()
+
+    def _update_core(self, batch):
+        """The device work of one update; returns the tensors the statistics
+        are read from (no Python-side state is touched, no host sync)."""
+        q1, q2, l1, l2 = self.update_q_func(batch)
+        entropy = self.update_policy_and_temperature(batch)
+        self.sync_target_network()
+        return q1, q2, l1, l2, entropy
 
     def update(self, experiences, errors_out=None):
         batch = batch_experiences(experiences, self.device, self.phi, self.gamma)
-        self.update_q_func(batch)
-        self.update_policy_and_temperature(batch)
-        self.sync_target_network()
+        q1, q2, l1, l2, entropy = self._update_core(batch)
+        self.n_policy_updates += 1
+        self.q1_record.extend(q1)
+        self.q2_record.extend(q2)
+        self.q_func1_loss_record.append(l1)
+        self.q_func2_loss_record.append(l2)
+        self.entropy_record.extend(entropy)
 
     def batch_select_greedy_action(self, batch_obs, deterministic=False):
         with torch.no_grad(), evaluating(self.policy):

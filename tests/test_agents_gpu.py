@@ -97,7 +97,7 @@ def test_ppo_on_device_env():
     normalizer = pnn.EmpiricalNormalization(obs_dim, clip_threshold=5)
     opt = torch.optim.Adam(model.parameters(), lr=3e-4, eps=1e-5)
     res = {}
-    for fused in (True, False):
+    for fused in (True, False, "graph"):
         set_random_seed(1)
         import copy
 
@@ -105,8 +105,8 @@ def test_ppo_on_device_env():
         agent = agents.PPO(m, torch.optim.Adam(m.parameters(), lr=3e-4, eps=1e-5),
                            obs_normalizer=nrm, gpu=0, gamma=0.995, lambd=0.95,
                            update_interval=16 * 32, minibatch_size=64, epochs=2, clip_eps=0.2,
-                           clip_eps_vf=None, entropy_coef=0.0)
-        agent.use_fused = fused
+                           clip_eps_vf=None, entropy_coef=0.0, cuda_graph=fused == "graph")
+        agent.use_fused = bool(fused)
         env = SyntheticContinuousVectorEnv(16, obs_dim, act_dim, device="cuda", seed=3,
                                            mean_episode_len=20)
         obs = env.reset()
@@ -119,9 +119,11 @@ def test_ppo_on_device_env():
         res[fused] = [p.detach().clone() for p in agent.model.parameters()]
         stats = dict(agent.get_statistics())
         assert np.isfinite(stats["average_value_loss"]) and np.isfinite(stats["explained_variance"])
-    # the fused GAE + loss kernels and the torch formulation give the same training run
-    for a, b in zip(res[True], res[False]):
+    # the fused GAE + loss kernels and the torch formulation give the same training run,
+    # and so does replaying the minibatch step as a CUDA graph
+    for a, b, c in zip(res[True], res[False], res["graph"]):
         torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-5)
+        torch.testing.assert_close(a, c, rtol=2e-3, atol=2e-5)
 
 
 def test_sac_on_device_env():
@@ -166,7 +168,9 @@ def test_sac_on_device_env():
         obs = env.reset(np.logical_not(d))
     stats = dict(agent.get_statistics())
     assert stats["n_updates"] > 300 and np.isfinite(stats["average_q1"])
+    assert np.isfinite(stats["average_q_func1_loss"]) and np.isfinite(stats["average_entropy"])
     assert len(agent.replay_buffer) == 8 * 60
+
 
 
 def test_iqn_on_device_replay_and_fused_loss():

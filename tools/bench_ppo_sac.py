@@ -50,13 +50,14 @@ def ppo():
     agent = agents.PPO(model, torch.optim.Adam(model.parameters(), lr=3e-4, eps=1e-5),
                        obs_normalizer=pnn.EmpiricalNormalization(obs_dim, clip_threshold=5),
                        gpu=0, gamma=0.995, lambd=0.95, update_interval=E * T, minibatch_size=64,
-                       epochs=10, clip_eps=0.2, clip_eps_vf=None, entropy_coef=0.0)
+                       epochs=10, clip_eps=0.2, clip_eps_vf=None, entropy_coef=0.0,
+                       cuda_graph=GRAPH)
     env = SyntheticContinuousVectorEnv(E, obs_dim, act_dim, device="cuda", seed=0)
     steps = 4 * T
     dt = timed(agent, env, steps, T)
     print(json.dumps({"workload": "PPO configs[3]: obs 376 act 17, 256 envs, T=8 (2048/update), "
                       "minibatch 64 x 10 epochs", "env_steps_per_sec": steps * E / dt,
-                      "updates": agent.n_updates, "seconds": dt}))
+                      "updates": agent.n_updates, "seconds": dt, "cuda_graph": GRAPH}))
 
 
 def sac():
@@ -91,6 +92,9 @@ def sac():
                       "updates_per_sec": steps * E / dt, "seconds": dt}))
 
 
+GRAPH = False
+
 if __name__ == "__main__":
-    ppo()
+    for GRAPH in (False, True):
+        ppo()
     sac()
