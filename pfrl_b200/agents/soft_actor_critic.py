@@ -20,7 +20,7 @@ from pfrl_b200.agents.dqn import _DeviceRing
 from pfrl_b200.replay_buffer import ReplayUpdater, batch_experiences
 from pfrl_b200.utils import clip_l2_grad_norm_
 from pfrl_b200.utils.batch_states import batch_states
-from pfrl_b200.utils.modes import evaluating
+from pfrl_b200.utils.modes import evaluating, no_distribution_validation
 from pfrl_b200.utils.copy_param import synchronize_parameters
 
 
@@ -64,7 +64,8 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
                  minibatch_size=100, update_interval=1, phi=lambda x: x, soft_update_tau=5e-3,
                  max_grad_norm=None, logger=getLogger(__name__), batch_states=batch_states,
                  burnin_action_func=None, initial_temperature=1.0, entropy_target=None,
-                 temperature_optimizer_lr=None, act_deterministically=True, grad_sync=None):
+                 temperature_optimizer_lr=None, act_deterministically=True, grad_sync=None,
+                 cuda_graph=False):
         self.policy = policy
         self.q_func1 = q_func1
         self.q_func2 = q_func2
@@ -118,6 +119,20 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
         self.q_func1_loss_record = _DeviceRing(100)
         self.q_func2_loss_record = _DeviceRing(100)
         self.n_policy_updates = 0
+        # Optional: replay the whole update (5 small networks, 4 optimizers, 2
+        # Polyak steps: ~300 launches of tiny kernels) as ONE CUDA graph.
+        self._graph_enabled = bool(cuda_graph) and self.device.type == "cuda" \
+            and grad_sync is None
+        self._graph = None
+        self._graph_warmup = 0
+        if self._graph_enabled:
+            for opt in (policy_optimizer, q_func1_optimizer, q_func2_optimizer,
+                        self.temperature_optimizer):
+                if opt is None:
+                    continue
+                for group in opt.param_groups:
+                    if "capturable" in group:
+                        group["capturable"] = True
 
     @property
     def temperature(self):
@@ -155,7 +170,10 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
         with torch.no_grad(), evaluating(self.policy), evaluating(self.target_q_func1), \
                 evaluating(self.target_q_func2):
             next_distrib = self.policy(next_state)
-            next_actions = next_distrib.sample()
+            # rsample() under no_grad draws the same law as sample() but skips
+            # torch.normal(mean, std)'s host-side `std.min() >= 0` check (a D2H
+            # sync per update in the reference, and illegal in graph capture)
+            next_actions = next_distrib.rsample()
             next_log_prob = next_distrib.log_prob(next_actions)
             next_q = torch.min(self.target_q_func1((next_state, next_actions)),
                                self.target_q_func2((next_state, next_actions)))
@@ -204,9 +222,32 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
         self.sync_target_network()
         return q1, q2, l1, l2, entropy
 
+    _GRAPH_KEYS = ("state", "next_state", "action", "reward", "discount", "is_state_terminal")
+
+    def _update_graphed(self, batch):
+        if self._graph is None:
+            if self._graph_warmup < 3:  # eager warm-up (optimizer state, cuBLAS workspaces)
+                self._graph_warmup += 1
+                return self._update_core(batch)
+            self._static_in = {k: batch[k].clone() for k in self._GRAPH_KEYS}
+            self._graph_shapes = {k: v.shape for k, v in self._static_in.items()}
+            torch.cuda.synchronize(self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with no_distribution_validation(), torch.cuda.graph(self._graph):
+                self._static_out = self._update_core(self._static_in)
+        if any(batch[k].shape != self._graph_shapes[k] for k in self._GRAPH_KEYS):
+            return self._update_core(batch)  # odd-sized batch: run eagerly
+        for k in self._GRAPH_KEYS:
+            self._static_in[k].copy_(batch[k])
+        self._graph.replay()  # capture only records: every update is a replay
+        return self._static_out
+
     def update(self, experiences, errors_out=None):
         batch = batch_experiences(experiences, self.device, self.phi, self.gamma)
-        q1, q2, l1, l2, entropy = self._update_core(batch)
+        if self._graph_enabled:
+            q1, q2, l1, l2, entropy = self._update_graphed(batch)
+        else:
+            q1, q2, l1, l2, entropy = self._update_core(batch)
         self.n_policy_updates += 1
         self.q1_record.extend(q1)
         self.q2_record.extend(q2)

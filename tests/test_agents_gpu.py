@@ -126,7 +126,8 @@ def test_ppo_on_device_env():
         torch.testing.assert_close(a, c, rtol=2e-3, atol=2e-5)
 
 
-def test_sac_on_device_env():
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sac_on_device_env(use_graph):
     from torch import distributions
 
     from pfrl_b200 import agents, nn as pnn
@@ -157,7 +158,8 @@ def test_sac_on_device_env():
         policy, q1, q2, torch.optim.Adam(policy.parameters(), lr=3e-4),
         torch.optim.Adam(q1.parameters(), lr=3e-4), torch.optim.Adam(q2.parameters(), lr=3e-4),
         ReplayBuffer(10 ** 4), gamma=0.99, gpu=0, replay_start_size=128, minibatch_size=64,
-        entropy_target=-act_dim, temperature_optimizer_lr=3e-4, phi=Identity())
+        entropy_target=-act_dim, temperature_optimizer_lr=3e-4, phi=Identity(),
+        cuda_graph=use_graph)
     env = SyntheticContinuousVectorEnv(8, obs_dim, act_dim, device="cuda", seed=1,
                                        mean_episode_len=30)
     obs = env.reset()
@@ -170,6 +172,8 @@ def test_sac_on_device_env():
     assert stats["n_updates"] > 300 and np.isfinite(stats["average_q1"])
     assert np.isfinite(stats["average_q_func1_loss"]) and np.isfinite(stats["average_entropy"])
     assert len(agent.replay_buffer) == 8 * 60
+    if use_graph:
+        assert agent._graph is not None  # the update really ran as a captured graph
 
 
 

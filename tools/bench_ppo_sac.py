@@ -82,14 +82,14 @@ def sac():
         policy, q1, q2, torch.optim.Adam(policy.parameters(), lr=3e-4),
         torch.optim.Adam(q1.parameters(), lr=3e-4), torch.optim.Adam(q2.parameters(), lr=3e-4),
         ReplayBuffer(10 ** 6), gamma=0.99, gpu=0, replay_start_size=2048, minibatch_size=1024,
-        entropy_target=-act_dim, temperature_optimizer_lr=3e-4, phi=Identity())
+        entropy_target=-act_dim, temperature_optimizer_lr=3e-4, phi=Identity(), cuda_graph=GRAPH)
     env = SyntheticContinuousVectorEnv(E, obs_dim, act_dim, device="cuda", seed=1)
     loop(agent, env, 2048 // E + 4)
     steps = 40
     dt = timed(agent, env, steps, 4)
     print(json.dumps({"workload": "SAC configs[4]: obs 17 act 6, 1M uniform replay, batch 1024, "
                       "update every env step", "env_steps_per_sec": steps * E / dt,
-                      "updates_per_sec": steps * E / dt, "seconds": dt}))
+                      "updates_per_sec": steps * E / dt, "seconds": dt, "cuda_graph": GRAPH}))
 
 
 GRAPH = False
@@ -97,4 +97,4 @@ GRAPH = False
 if __name__ == "__main__":
     for GRAPH in (False, True):
         ppo()
-    sac()
+        sac()
