@@ -352,7 +352,6 @@ def main():
     rng = np.random.RandomState(100 + rank)
     T = cap + N_STEP - 1
     chunk = 1 << 17
-    first = True
     t_fill = time.perf_counter()
     done = 0
     while done < T:
@@ -366,7 +365,6 @@ def main():
         term[-1] = True  # close the segment so that its tail is emitted
         buf.append_trajectory(frames, acts, rews, term)
         done += m
-        first = False
     # non-uniform priorities so that the tree descent is not degenerate
     n_pri = 64
     for _ in range(n_pri):

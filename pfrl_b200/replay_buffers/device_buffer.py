@@ -230,14 +230,17 @@ class DeviceNStepBuffer:
             terminals = np.zeros(T, dtype=bool)
         terminals = np.asarray(terminals, dtype=bool)
         if self.store is None:
-            class _Probe:  # LazyFrames-like layout probe
-                pass
-            probe = _Probe()
-            probe._frames = [frames[i][None] if frames[i].dim() == 2 else frames[i]
-                             for i in range(stack)] if isinstance(frames, torch.Tensor) else \
-                [np.asarray(frames[i])[None] if np.asarray(frames[i]).ndim == 2 else np.asarray(frames[i])
-                 for i in range(stack)]
-            self._create_store(probe, actions[0])
+            # infer the layout from a LazyFrames-like view of the first observation
+            # (frames get a leading stack axis: (84, 84) -> (1, 84, 84))
+            def _as_part(f):
+                if isinstance(f, torch.Tensor):
+                    return f[None] if f.dim() == 2 else f
+                f = np.asarray(f)
+                return f[None] if f.ndim == 2 else f
+
+            first_obs = type("_FirstObs", (), {})()
+            first_obs._frames = [_as_part(frames[i]) for i in range(stack)]
+            self._create_store(first_obs, actions[0])
         lay = self.layout
         n_frames = frames.shape[0]
         assert n_frames <= self._part_capacity

@@ -175,9 +175,6 @@ def test_parallel_sampler_matches_frozen_descent():
     gi, gp = store.sample(u, mode=1)
     gi = gi.cpu().numpy()
     # each draw alone must equal the oracle's first draw with that u
-    leaves = store.read_priorities()
-    cum = np.cumsum(leaves)
-    tot = ora.total()
     for k in range(0, 256, 17):
         oi, op, _, _ = ora.sample_indices(1, u[k:k + 1])
         ora.set_last_priority(op)  # restore
