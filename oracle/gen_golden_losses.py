@@ -158,6 +158,7 @@ def main(out_dir):
         g["ppo_mean_std"] = np.array([float(mean_a), float(std_a)], dtype=np.float32)
 
     agent_losses(out_dir)
+    normalizer(out_dir)
     g["numpy_version"] = np.array(np.__version__)
     np.savez_compressed(os.path.join(out_dir, "losses.npz"), **g)
     print("wrote losses.npz with", len(g), "arrays")
@@ -218,3 +219,23 @@ def agent_losses(out_dir):
         q_functions.DistributionalFCStateQFunctionWithDiscreteAction(obs, nA, 21, -2, 2, 32, 2))
     np.savez_compressed(os.path.join(out_dir, "agent_losses.npz"), **g)
     print("wrote agent_losses.npz with", len(g), "arrays")
+
+
+def normalizer(out_dir):
+    """EmpiricalNormalization (pfrl/nn/empirical_normalization.py:6-109) on a
+    fixed sequence of batches."""
+    import torch
+    from pfrl.nn import EmpiricalNormalization
+
+    rng = np.random.RandomState(3)
+    en = EmpiricalNormalization(7, clip_threshold=5)
+    xs = [(rng.randn(n, 7) * s + m).astype(np.float32)
+          for n, s, m in ((16, 1.0, 0.0), (1, 3.0, 2.0), (64, 0.5, -1.0), (5, 10.0, 4.0))]
+    outs = [en(torch.tensor(x), update=True).numpy() for x in xs]
+    probe = rng.randn(9, 7).astype(np.float32) * 4
+    np.savez_compressed(
+        os.path.join(out_dir, "empirical_normalization.npz"),
+        **{"x%d" % i: x for i, x in enumerate(xs)}, **{"y%d" % i: y for i, y in enumerate(outs)},
+        probe=probe, probe_out=en(torch.tensor(probe), update=False).numpy(),
+        mean=en.mean.numpy(), std=en.std.numpy(), count=np.int64(en.count.item()))
+    print("wrote empirical_normalization.npz")
