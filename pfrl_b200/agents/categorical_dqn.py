@@ -71,7 +71,7 @@ class CategoricalDQN(dqn.DQN):
         batch_q = qout.evaluate_actions_as_distribution(actions)
         with torch.no_grad():
             batch_q_target = self._compute_target_values(exp_batch)
-            self.q_record.extend(qout.evaluate_actions(actions))
+            self._last_q = qout.evaluate_actions(actions).detach()
         return batch_q, batch_q_target
 
     def _compute_loss(self, exp_batch, want_errors=False):
@@ -96,7 +96,7 @@ class CategoricalDQN(dqn.DQN):
         y = qout.evaluate_actions_as_distribution(actions)
         with torch.no_grad():
             next_p, z_values = self._next_distribution(exp_batch)
-            self.q_record.extend(qout.evaluate_actions(actions))
+            self._last_q = qout.evaluate_actions(actions).detach()
         v_min = float(z_values[0]) if not hasattr(self, "_z_cache") else self._z_cache[0]
         if not hasattr(self, "_z_cache"):
             self._z_cache = (float(z_values[0]), float(z_values[-1]), int(z_values.numel()))

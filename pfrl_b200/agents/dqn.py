@@ -122,7 +122,7 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
                  target_update_method="hard", soft_update_tau=1e-2, n_times_update=1,
                  batch_accumulator="mean", episodic_update_len=None,
                  logger=getLogger(__name__), batch_states=batch_states, recurrent=False,
-                 max_grad_norm=None, grad_sync=None):
+                 max_grad_norm=None, grad_sync=None, cuda_graph=False):
         if recurrent:
             raise NotImplementedError("recurrent DQN is out of scope of pfrl_b200")
         self.model = q_function
@@ -170,6 +170,17 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
         self.loss_record = _DeviceRing(100)
         self.batch_last_obs = []
         self.batch_last_action = []
+        # Optional: replay forward(s) + fused loss + backward + clip + optimizer
+        # step as ONE CUDA graph (pays off when the minibatch is small and the
+        # update is launch-bound, e.g. Nature-DQN at batch 32).
+        self._graph_enabled = bool(cuda_graph) and self.device.type == "cuda" \
+            and grad_sync is None
+        self._graph = None
+        self._graph_warmup = 0
+        if self._graph_enabled:
+            for group in optimizer.param_groups:
+                if "capturable" in group:
+                    group["capturable"] = True
         if (self.replay_buffer.capacity is not None
                 and self.replay_buffer.capacity < self.replay_updater.replay_start_size):
             raise ValueError("Replay start size cannot exceed replay buffer capacity.")
@@ -196,15 +207,28 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
                     [e[0]["weight"] for e in experiences], device=self.device,
                     dtype=torch.float32)
         want_list = errors_out is not None
-        loss, delta = self._compute_loss(exp_batch, want_errors=has_weight or want_list)
+        want_errors = has_weight or want_list
+        if self._graph_enabled:
+            loss, delta = self._learn_graphed(exp_batch, want_errors)
+        else:
+            loss, delta = self._learn(exp_batch, want_errors)
         if want_list:
             del errors_out[:]
             errors_out.extend(delta.detach().cpu().numpy())
         if has_weight:
             assert isinstance(self.replay_buffer, PrioritizedReplayBuffer)
-            # device tensor in, device trees updated: no host round trip
+            # device tensor in, device trees updated: no host round trip.  (The
+            # reference calls update_errors between forward and backward,
+            # dqn.py:356; the priorities only depend on the forward pass.)
             self.replay_buffer.update_errors(delta.detach())
         self.loss_record.append(loss.detach())
+        self.q_record.extend(self._last_q)
+        self.optim_t += 1
+
+    def _learn(self, exp_batch, want_errors):
+        """loss -> backward -> (all-reduce) -> clip -> optimizer step; touches no
+        Python-side state, so it can be captured in a CUDA graph."""
+        loss, delta = self._compute_loss(exp_batch, want_errors=want_errors)
         self.optimizer.zero_grad()
         loss.backward()
         if self.grad_sync is not None:
@@ -212,7 +236,29 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
         if self.max_grad_norm is not None:
             clip_l2_grad_norm_(self.model.parameters(), self.max_grad_norm)
         self.optimizer.step()
-        self.optim_t += 1
+        return loss.detach(), delta
+
+    def _learn_graphed(self, exp_batch, want_errors):
+        sig = tuple(sorted((k, tuple(v.shape), v.dtype) for k, v in exp_batch.items())) + (
+            want_errors,)
+        if self._graph is None:
+            if self._graph_warmup < 3:  # eager warm-up: optimizer state, cuDNN / cuBLAS plans
+                self._graph_warmup += 1
+                return self._learn(exp_batch, want_errors)
+            self._graph_sig = sig
+            self._static_in = {k: v.clone() for k, v in exp_batch.items()}
+            torch.cuda.synchronize(self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._static_out = self._learn(self._static_in, want_errors)
+            self._static_q = self._last_q
+        if sig != self._graph_sig:
+            return self._learn(exp_batch, want_errors)  # different batch layout: run eagerly
+        for k, v in exp_batch.items():
+            self._static_in[k].copy_(v)
+        self._graph.replay()  # capture only records: every update is a replay
+        self._last_q = self._static_q
+        return self._static_out
 
     def _next_q(self, exp_batch):
         """Value of the next state used in the target: max_a Q_target(s', a)."""
@@ -245,10 +291,10 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
                 exp_batch["discount"], exp_batch["is_state_terminal"],
                 exp_batch.get("weights"), clip_delta=self.clip_delta,
                 mean=self.batch_accumulator == "mean")
-            self.q_record.extend(y)
+            self._last_q = y.detach()
             return loss, delta
         y, t = self._compute_y_and_t(exp_batch)
-        self.q_record.extend(y)
+        self._last_q = y.detach()
         delta = None
         if want_errors:
             delta = torch.abs(y.detach() - t)

@@ -112,7 +112,7 @@ class IQN(dqn.DQN):
         taus = self._taus(batch_size, self.quantile_thresholds_N)
         av = tau2av(taus)
         y = av.evaluate_actions_as_quantiles(exp_batch["action"])
-        self.q_record.extend(av.q_values.detach())
+        self._last_q = av.q_values.detach()
         return y, taus
 
     def _compute_loss(self, exp_batch, want_errors=False):

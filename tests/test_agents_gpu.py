@@ -224,3 +224,41 @@ def test_iqn_on_device_replay_and_fused_loss():
         obs = env.reset(np.logical_not(d))
     stats = dict(agent.get_statistics())
     assert stats["n_updates"] > 100 and np.isfinite(stats["average_loss"])
+
+
+def test_dqn_update_as_cuda_graph_matches_eager():
+    """cuda_graph=True replays forward + fused TD loss + backward + Adam as one
+    graph: same parameters as the eager path after the same seeded run."""
+    from pfrl_b200 import agents, explorers, q_functions
+    from pfrl_b200.envs import SyntheticContinuousVectorEnv
+    from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
+    from pfrl_b200.utils import set_random_seed
+    from pfrl_b200.utils.phi import Identity
+
+    res = {}
+    for graph in (False, True):
+        set_random_seed(3)
+        q = q_functions.FCStateQFunctionWithDiscreteAction(12, 4, 64, 2)
+        agent = agents.DoubleDQN(
+            # capturable=True in BOTH runs: Adam's capturable path keeps `step` and the
+            # bias corrections on the device (fp32), the default path computes them on the
+            # host in fp64 -- a 1e-7 difference that prioritized sampling would amplify
+            q.cuda(), torch.optim.Adam(q.parameters(), lr=1e-3, capturable=True),
+            PrioritizedReplayBuffer(4096, num_steps=3),
+            0.99, explorers.ConstantEpsilonGreedy(0.3, lambda: np.random.randint(4)), gpu=0,
+            replay_start_size=64, minibatch_size=32, target_update_interval=40, phi=Identity(),
+            cuda_graph=graph)
+        env = SyntheticContinuousVectorEnv(4, 12, 1, device="cuda", seed=5, mean_episode_len=20)
+        obs = env.reset()
+        for _ in range(80):
+            a = agent.batch_act(obs)
+            obs, r, d, info = env.step(a)
+            agent.batch_observe(obs, r, d, np.zeros(4, dtype=bool))
+            obs = env.reset(np.logical_not(d))
+        assert agent.optim_t > 200
+        assert (agent._graph is not None) == graph
+        res[graph] = ([p.detach().clone() for p in agent.model.parameters()],
+                      dict(agent.get_statistics()))
+    for a, b in zip(res[False][0], res[True][0]):
+        torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
+    assert abs(res[False][1]["average_loss"] - res[True][1]["average_loss"]) < 1e-3

@@ -1,7 +1,9 @@
-"""Secondary workloads (BASELINE configs[3], configs[4]) on one GPU: PPO on a
+"""Secondary workloads (BASELINE configs[1], [3], [4]) on one GPU: Nature-DQN
+with PER at batch 32 (configs[1]), PPO on a
 synthetic Humanoid-shaped env (obs 376, act 17, 256 envs, lambda .95) and SAC
 (obs 17, act 6, 1M replay, batch 1024).  Prints one JSON line per workload.
-Dev / evidence tool: python tools/bench_ppo_sac.py  (GPU box)."""
+Each is run eagerly and with its update captured as a CUDA graph.
+Dev / evidence tool: python tools/bench_secondary.py  (GPU box)."""
 import json
 import os
 import sys
@@ -34,6 +36,32 @@ def timed(agent, env, steps, warm):
     loop(agent, env, steps)
     torch.cuda.synchronize()
     return time.perf_counter() - t0
+
+
+def dqn():
+    """configs[1]: DQN, synthetic 84x84x4 frames, PER (200k here), batch 32."""
+    from pfrl_b200 import explorers, q_functions
+    from pfrl_b200.envs import SyntheticAtariVectorEnv
+    from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
+    from pfrl_b200.utils.phi import ScaleU8
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    q = nn.Sequential(pnn.LargeAtariCNN(), nn.Linear(512, 18),
+                      q_functions.DiscreteActionValueHead()).cuda()
+    rbuf = PrioritizedReplayBuffer(200000, alpha=0.6, beta0=0.4, betasteps=10 ** 6, num_steps=1)
+    agent = agents.DQN(q, torch.optim.RMSprop(q.parameters(), lr=2.5e-4, alpha=0.95, eps=1e-2),
+                       rbuf, 0.99, explorers.ConstantEpsilonGreedy(0.1, lambda: np.random.randint(18)),
+                       gpu=0, replay_start_size=1000, minibatch_size=32, update_interval=4,
+                       target_update_interval=10000, phi=ScaleU8(), cuda_graph=GRAPH)
+    env = SyntheticAtariVectorEnv(16, device="cuda", seed=0)
+    loop(agent, env, 1000 // 16 + 8)
+    steps = 60
+    n0 = agent.optim_t
+    dt = timed(agent, env, steps, 4)
+    print(json.dumps({"workload": "DQN configs[1]: Nature CNN, PER, batch 32, update_interval 4, "
+                      "16 GPU envs", "env_steps_per_sec": steps * 16 / dt,
+                      "updates_per_sec": (agent.optim_t - n0) / dt, "cuda_graph": GRAPH}))
 
 
 def ppo():
@@ -96,5 +124,6 @@ GRAPH = False
 
 if __name__ == "__main__":
     for GRAPH in (False, True):
+        dqn()
         ppo()
         sac()
