@@ -79,3 +79,23 @@ class Greedy(explorer.Explorer):
 
     def __repr__(self):
         return "Greedy()"
+
+
+class AdditiveGaussian(explorer.Explorer):
+    """greedy action + N(0, scale^2) noise drawn from numpy's global stream,
+    optionally clipped to [low, high] (pfrl/explorers/additive_gaussian.py)."""
+
+    def __init__(self, scale, low=None, high=None):
+        self.scale = scale
+        self.low = low
+        self.high = high
+
+    def select_action(self, t, greedy_action_func, action_value=None):
+        a = greedy_action_func()
+        noisy = a + np.random.normal(scale=self.scale, size=a.shape).astype(np.float32)
+        if self.low is None and self.high is None:
+            return noisy
+        return np.clip(noisy, self.low, self.high)
+
+    def __repr__(self):
+        return "AdditiveGaussian(scale={}, low={}, high={})".format(self.scale, self.low, self.high)

@@ -1,4 +1,5 @@
 from pfrl_b200.policies.heads import (  # NOQA
+    DeterministicHead,
     GaussianHeadWithDiagonalCovariance,
     GaussianHeadWithFixedCovariance,
     GaussianHeadWithStateIndependentCovariance,

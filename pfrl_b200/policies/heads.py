@@ -8,6 +8,16 @@ import torch
 from torch import nn
 
 
+class DeterministicHead(nn.Module):
+    """action -> point-mass distribution at that action (DDPG / TD3 policies;
+    reference: pfrl/policies/deterministic_policy.py)."""
+
+    def forward(self, loc):
+        from pfrl_b200.distributions import Delta
+
+        return torch.distributions.Independent(Delta(loc=loc), 1)
+
+
 class SoftmaxCategoricalHead(nn.Module):
     """Unnormalised log-probabilities -> ``Categorical`` over discrete actions."""
 

@@ -210,3 +210,41 @@ def test_train_agent_batch_call_contract(tmp_path):
     assert agent.save.call_count == 1
     args = agent.batch_observe.call_args_list[2][0]
     assert list(args[3]) == [False, True]
+
+
+@pytest.mark.parametrize("kind", ["td3", "ddpg"])
+def test_td3_and_ddpg_learn_chain(kind, tmp_path):
+    set_random_seed(0)
+
+    def pol():
+        return nn.Sequential(nn.Linear(5, 32), nn.ReLU(), nn.Linear(32, 1), nn.Tanh(),
+                             policies.DeterministicHead())
+
+    def qf():
+        return nn.Sequential(pnn.ConcatObsAndAction(), nn.Linear(6, 32), nn.ReLU(),
+                             nn.Linear(32, 1))
+
+    ex = explorers.AdditiveGaussian(scale=0.3, low=-1, high=1)
+    phi = lambda x: x.astype(np.float32, copy=False)  # noqa: E731
+    burn = lambda: np.random.uniform(-1, 1, size=1).astype(np.float32)  # noqa: E731
+    if kind == "td3":
+        p, q1, q2 = pol(), qf(), qf()
+        agent = agents.TD3(p, q1, q2, torch.optim.Adam(p.parameters(), lr=3e-3),
+                           torch.optim.Adam(q1.parameters(), lr=3e-3),
+                           torch.optim.Adam(q2.parameters(), lr=3e-3), HostReplayBuffer(5000),
+                           0.95, ex, replay_start_size=64, minibatch_size=32, phi=phi,
+                           burnin_action_func=burn)
+    else:
+        p, q = pol(), qf()
+        agent = agents.DDPG(p, q, torch.optim.Adam(p.parameters(), lr=3e-3),
+                            torch.optim.Adam(q.parameters(), lr=3e-3), HostReplayBuffer(5000),
+                            0.95, ex, replay_start_size=64, minibatch_size=32, phi=phi,
+                            target_update_method="soft", target_update_interval=1,
+                            soft_update_tau=0.05, burnin_action_func=burn)
+    env = SerialVectorEnv([ChainEnv(continuous=True, seed=i) for i in range(2)])
+    experiments.train_agent_batch(agent, env, 1500, str(tmp_path))
+    assert greedy_return(agent, continuous=True) > 0.9
+    stats = dict(agent.get_statistics())
+    assert all(np.isfinite(v) for v in stats.values())
+    agent.save(str(tmp_path / "ckpt"))
+    assert os.path.exists(str(tmp_path / "ckpt" / ("policy.pt" if kind == "td3" else "model.pt")))

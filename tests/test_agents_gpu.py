@@ -262,3 +262,38 @@ def test_dqn_update_as_cuda_graph_matches_eager():
     for a, b in zip(res[False][0], res[True][0]):
         torch.testing.assert_close(a, b, rtol=1e-3, atol=1e-5)
     assert abs(res[False][1]["average_loss"] - res[True][1]["average_loss"]) < 1e-3
+
+
+def test_td3_on_device_replay():
+    from pfrl_b200 import agents, explorers, nn as pnn, policies
+    from pfrl_b200.envs import SyntheticContinuousVectorEnv
+    from pfrl_b200.replay_buffers import ReplayBuffer
+    from pfrl_b200.utils import set_random_seed
+    from pfrl_b200.utils.phi import Identity
+
+    set_random_seed(0)
+    obs_dim, act_dim = 17, 6
+    p = nn.Sequential(nn.Linear(obs_dim, 64), nn.ReLU(), nn.Linear(64, act_dim), nn.Tanh(),
+                      policies.DeterministicHead())
+
+    def qf():
+        return nn.Sequential(pnn.ConcatObsAndAction(), nn.Linear(obs_dim + act_dim, 64), nn.ReLU(),
+                             nn.Linear(64, 1))
+
+    q1, q2 = qf(), qf()
+    agent = agents.TD3(
+        p, q1, q2, torch.optim.Adam(p.parameters(), lr=3e-4),
+        torch.optim.Adam(q1.parameters(), lr=3e-4), torch.optim.Adam(q2.parameters(), lr=3e-4),
+        ReplayBuffer(10 ** 4), 0.99, explorers.AdditiveGaussian(0.1, -1, 1), gpu=0,
+        replay_start_size=128, minibatch_size=64, phi=Identity())
+    env = SyntheticContinuousVectorEnv(8, obs_dim, act_dim, device="cuda", seed=1,
+                                       mean_episode_len=30)
+    obs = env.reset()
+    for _ in range(50):
+        a = agent.batch_act(obs)
+        obs, r, d, info = env.step(a)
+        agent.batch_observe(obs, r, d, np.zeros(8, dtype=bool))
+        obs = env.reset(np.logical_not(d))
+    stats = dict(agent.get_statistics())
+    assert stats["q_func_n_updates"] > 200 and stats["policy_n_updates"] > 100
+    assert np.isfinite(stats["average_q1"]) and np.isfinite(stats["average_policy_loss"])
