@@ -1,0 +1,1 @@
+from pfrl_b200.wrappers.vector_frame_stack import VectorEnvWrapper, VectorFrameStack  # NOQA

@@ -96,3 +96,42 @@ def test_train_agent_batch_with_evaluation_writes_scores(tmp_path):
     assert len(rows) == 4 and rows[0].split("\t")[8:] == [n for n, _ in agent.get_statistics()]
     assert os.path.isdir(os.path.join(str(tmp_path), "best"))
     assert os.path.isdir(os.path.join(str(tmp_path), "300_finish"))
+
+
+def test_vector_frame_stack_shares_frame_objects():
+    """reference: tests/wrappers_tests/test_vector_frame_stack.py (needs gym
+    there); here: frames are shared between consecutive observations and a
+    reset repeats the first frame k times."""
+    from pfrl_b200.envs import SerialVectorEnv
+    from pfrl_b200.wrappers import VectorFrameStack
+
+    class ImgEnv:
+        def __init__(self, seed):
+            self.rng = np.random.RandomState(seed)
+            self.t = 0
+
+        def reset(self):
+            self.t = 0
+            return self.rng.randint(0, 256, size=(1, 6, 6)).astype(np.uint8)
+
+        def step(self, a):
+            self.t += 1
+            return (self.rng.randint(0, 256, size=(1, 6, 6)).astype(np.uint8), 1.0, self.t == 5, {})
+
+        def close(self):
+            pass
+
+    venv = VectorFrameStack(SerialVectorEnv([ImgEnv(i) for i in range(3)]), k=4)
+    obs = venv.reset()
+    assert len(obs) == 3 and np.asarray(obs[0]).shape == (4, 6, 6)
+    assert all(f is obs[0]._frames[0] for f in obs[0]._frames)  # first frame repeated
+    obs2, r, d, info = venv.step([0, 0, 0])
+    assert obs2[1]._frames[:3] == obs[1]._frames[1:] or all(
+        a is b for a, b in zip(obs2[1]._frames[:3], obs[1]._frames[1:]))
+    assert obs2[1]._frames[3] is not obs[1]._frames[3]
+    for _ in range(4):
+        obs2, r, d, info = venv.step([0, 0, 0])
+    assert all(d)
+    obs3 = venv.reset(np.logical_not(d))
+    assert all(f is obs3[2]._frames[0] for f in obs3[2]._frames)
+    assert venv.num_envs == 3
