@@ -35,7 +35,7 @@ def make_state(sid, shape):
 def gen_per_trace(name, seed, capacity, num_steps, n_envs, steps, batch, alpha, beta0,
                   betasteps, normalize_by_max, gamma, obs_shape=(4, 6, 6), lazy=False):
     import torch
-    import pfrl
+
     from pfrl.replay_buffer import batch_experiences
     from pfrl.replay_buffers import PrioritizedReplayBuffer
     from pfrl.wrappers.atari_wrappers import LazyFrames

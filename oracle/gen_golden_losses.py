@@ -168,7 +168,7 @@ def agent_losses(out_dir):
     """End-to-end _compute_loss of the reference's agents on a fixed batch and
     fixed weights (fp32, CPU): pins 'fp32 losses within 1e-5'."""
     import torch
-    import pfrl
+
     from pfrl import agents, explorers, q_functions, replay_buffers
 
     rng = np.random.RandomState(7)

@@ -12,7 +12,6 @@ from torch import nn
 from pfrl_b200.action_value import QuantileDiscreteActionValue
 from pfrl_b200.agents import dqn
 from pfrl_b200.ops import losses as fused
-from pfrl_b200.utils.modes import evaluating
 
 
 def cosine_basis_functions(x, n_basis_functions=64):

@@ -10,7 +10,6 @@ Polyak steps are multi-tensor launches.
 import copy
 from logging import getLogger
 
-import numpy as np
 import torch
 from torch import nn
 from torch.nn import functional as F

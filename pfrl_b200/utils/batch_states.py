@@ -4,7 +4,6 @@ Mirrors pfrl/utils/batch_states.py:18-36 (phi per observation, collate, move
 to device).  Observations that already live on the device (tensors produced
 by the GPU vector envs) take a fused path with no host round trip.
 """
-import numpy as np
 import torch
 from torch.utils.data._utils.collate import default_collate
 

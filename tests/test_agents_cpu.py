@@ -9,7 +9,6 @@ import pytest
 import torch
 from torch import nn
 
-import pfrl_b200
 from pfrl_b200 import agents, experiments, explorers, nn as pnn, policies, q_functions
 from pfrl_b200.envs import ChainEnv, SerialVectorEnv
 from pfrl_b200.replay_buffers import HostReplayBuffer
