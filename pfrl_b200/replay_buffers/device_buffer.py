@@ -567,7 +567,8 @@ class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
         self.beta = min(1.0, self.beta + self.beta_add)  # prioritized.py:65
         self._waiting = True
         self._last_n = n
-        return DeviceExperiences(self, n, index=index, weights=weights, pending=True)
+        self._last_handle = DeviceExperiences(self, n, index=index, weights=weights, pending=True)
+        return self._last_handle
 
     def update_errors(self, errors):
         """TD errors of the last sample -> new priorities.
@@ -590,3 +591,7 @@ class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
             assert all(p > 0.0 for p in pr)  # collections/prioritized.py:109
             self.store.update_priorities(np.asarray(pr, dtype=np.float64))
         self._waiting = False
+        # the handle's "slots of the pending sample" are gone; it can still be
+        # gathered / materialised through its logical indices
+        self._last_handle.pending = False
+        self._last_handle = None
