@@ -159,6 +159,7 @@ def main(out_dir):
 
     agent_losses(out_dir)
     normalizer(out_dir)
+    a2c_trace(out_dir)
     g["numpy_version"] = np.array(np.__version__)
     np.savez_compressed(os.path.join(out_dir, "losses.npz"), **g)
     print("wrote losses.npz with", len(g), "arrays")
@@ -239,3 +240,55 @@ def normalizer(out_dir):
         probe=probe, probe_out=en(torch.tensor(probe), update=False).numpy(),
         mean=en.mean.numpy(), std=en.std.numpy(), count=np.int64(en.count.item()))
     print("wrote empirical_normalization.npz")
+
+
+def a2c_trace(out_dir):
+    """A seeded A2C run of the reference (pfrl/agents/a2c.py:14-310) on scripted
+    observations / rewards / dones: the sampled actions, the three running
+    statistics after every update and the final parameters."""
+    import torch
+    from torch import nn
+
+    import pfrl
+    from pfrl.agents import a2c
+    from pfrl.policies import GaussianHeadWithStateIndependentCovariance, SoftmaxCategoricalHead
+
+    rng = np.random.RandomState(5)
+    N, obs, steps = 6, 9, 23
+    g = dict(obs=rng.randn(steps + 1, N, obs).astype(np.float32),
+             reward=rng.randn(steps, N).astype(np.float32),
+             done=(rng.rand(steps, N) < 0.15))
+
+    def make(kind):
+        torch.manual_seed(31)
+        if kind == "discrete":
+            head = nn.Sequential(nn.Linear(16, 4), SoftmaxCategoricalHead())
+        else:
+            head = nn.Sequential(nn.Linear(16, 3), GaussianHeadWithStateIndependentCovariance(
+                action_size=3, var_type="diagonal", var_func=lambda x: torch.exp(2 * x),
+                var_param_init=0))
+        return nn.Sequential(nn.Linear(obs, 16), nn.Tanh(),
+                             pfrl.nn.Branched(head, nn.Linear(16, 1)))
+
+    for kind, kw in (("discrete", dict(use_gae=False, max_grad_norm=0.5)),
+                     ("gaussian", dict(use_gae=True, tau=0.9, max_grad_norm=None))):
+        model = make(kind)
+        for k, v in model.state_dict().items():
+            g["%s_init_%s" % (kind, k)] = v.numpy().copy()
+        opt = torch.optim.RMSprop(model.parameters(), lr=7e-3, eps=1e-5, alpha=0.99)
+        agent = a2c.A2C(model, opt, gamma=0.97, num_processes=N, update_steps=4,
+                        average_actor_loss_decay=0.0, average_entropy_decay=0.0,
+                        average_value_decay=0.0, **kw)
+        torch.manual_seed(77)
+        actions, stats = [], []
+        for t in range(steps):
+            actions.append(agent.batch_act(list(g["obs"][t])))
+            agent.batch_observe(list(g["obs"][t + 1]), list(g["reward"][t]), list(g["done"][t]),
+                                [False] * N)
+            stats.append([v for _, v in agent.get_statistics()])
+        g[kind + "_actions"] = np.asarray(actions)
+        g[kind + "_stats"] = np.asarray(stats, dtype=np.float64)
+        for k, v in model.state_dict().items():
+            g["%s_final_%s" % (kind, k)] = v.numpy().copy()
+    np.savez_compressed(os.path.join(out_dir, "a2c_trace.npz"), **g)
+    print("wrote a2c_trace.npz with", len(g), "arrays")
