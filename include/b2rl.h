@@ -190,6 +190,11 @@ int b2rl_per_get_info(b2rl_replay *h, b2rl_per_info *out_host, void *stream);
 int b2rl_per_read_priorities(b2rl_replay *h, int64_t first, int64_t n,
                              double *out_host, void *stream);
 
+/* Restore max_priority when a checkpoint is loaded: the reference pickles the
+ * whole PrioritizedBuffer, max_priority included (pfrl/replay_buffers/
+ * replay_buffer.py:85-94; pfrl/collections/prioritized.py:32). Synchronises. */
+int b2rl_per_set_max_priority(b2rl_replay *h, double max_priority, void *stream);
+
 /* ------------------------------------------------------------------------
  * Minibatch gather; replaces batch_experiences (pfrl/replay_buffer.py:
  * 157-212) + batch_states (pfrl/utils/batch_states.py:18-36) + the H2D copy.

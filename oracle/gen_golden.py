@@ -180,10 +180,90 @@ def gen_uniform_trace(name, seed, capacity, num_steps, steps, batch, gamma):
     print("wrote", name, "samples:", len(sizes))
 
 
+def gen_reference_checkpoints():
+    """replay_buffer.pkl files exactly as the reference writes them
+    (replay_buffers/replay_buffer.py:85-87) plus what the reference says they
+    hold: batch_experiences over every experience in queue order, leaf
+    priorities, max_priority."""
+    import torch
+
+    from pfrl.replay_buffer import batch_experiences
+    from pfrl.replay_buffers import PrioritizedReplayBuffer, ReplayBuffer
+    from pfrl.wrappers.atari_wrappers import LazyFrames
+
+    phi = lambda x: np.asarray(x, dtype=np.float32)  # noqa: E731
+    cpu = torch.device("cpu")
+
+    def expected(memory_items, gamma):
+        b = batch_experiences(list(memory_items), cpu, phi, gamma)
+        return {k: v.numpy() for k, v in b.items()}
+
+    # uniform, 3-step, float32 vector observations, two interleaved env ids
+    rng = np.random.RandomState(41)
+    rbuf = ReplayBuffer(capacity=50, num_steps=3)
+    obs = [rng.randn(4).astype(np.float32) for _ in range(2)]
+    for t in range(90):
+        e = t % 2
+        nxt = rng.randn(4).astype(np.float32)
+        done = rng.rand() < 0.12
+        rbuf.append(obs[e], np.float32(rng.randn(2)), float(rng.randn()), nxt,
+                    is_state_terminal=done, env_id=e)
+        if done or rng.rand() < 0.05:
+            rbuf.stop_current_episode(env_id=e)
+            nxt = rng.randn(4).astype(np.float32)
+        obs[e] = nxt
+    rbuf.save(os.path.join(OUT, "ref_uniform_3step.pkl"))
+    exp = expected(rbuf.memory, 0.9)
+    np.savez_compressed(os.path.join(OUT, "ref_uniform_3step_expected.npz"),
+                        n=len(rbuf), capacity=50, **exp)
+
+    # prioritised, 1-step, LazyFrames uint8 observations sharing frames
+    rng = np.random.RandomState(42)
+    np.random.seed(42)
+    rbuf = PrioritizedReplayBuffer(capacity=40, alpha=0.6, beta0=0.4, betasteps=100, num_steps=1)
+    sid = 0
+
+    def fresh():
+        nonlocal sid
+        sid += 1
+        return make_state(sid, (1, 6, 6))
+
+    frames = [fresh() for _ in range(4)]
+    cur = LazyFrames(list(frames), stack_axis=0)
+    for t in range(75):
+        done = rng.rand() < 0.1
+        frames = frames[1:] + [fresh()]
+        nxt = LazyFrames(list(frames), stack_axis=0)
+        rbuf.append(cur, int(rng.randint(6)), float(rng.choice([-1.0, 0.0, 1.0])), nxt,
+                    is_state_terminal=done)
+        cur = nxt
+        if done:
+            rbuf.stop_current_episode()
+            frames = [fresh() for _ in range(4)]
+            cur = LazyFrames(list(frames), stack_axis=0)
+        if t >= 20 and t % 5 == 0:
+            rbuf.sample(8)
+            rbuf.update_errors([float(x) for x in np.abs(rng.randn(8)) * 3])
+    rbuf.save(os.path.join(OUT, "ref_per_lazyframes.pkl"))
+    sums = rbuf.memory.priority_sums
+    pri = []
+    for i in range(len(rbuf)):
+        v = sums._write(i, 0.0)
+        sums._write(i, v)
+        pri.append(v)
+    exp = expected(rbuf.memory.data, 0.99)
+    np.savez_compressed(os.path.join(OUT, "ref_per_lazyframes_expected.npz"),
+                        n=len(rbuf), capacity=40, priority=np.asarray(pri, dtype=np.float64),
+                        max_priority=np.float64(rbuf.memory.max_priority),
+                        total=np.float64(sums.sum()), **exp)
+    print("wrote reference checkpoints:", len(rbuf), "PER experiences")
+
+
 def main():
     import_reference()
     os.makedirs(OUT, exist_ok=True)
     print("numpy", np.__version__)
+    gen_reference_checkpoints()
     gen_per_trace("per_trace_1step", seed=11, capacity=300, num_steps=1, n_envs=1, steps=900,
                   batch=16, alpha=0.6, beta0=0.4, betasteps=200, normalize_by_max=True,
                   gamma=0.99)

@@ -131,6 +131,7 @@ SIGNATURES = {
     "b2rl_per_update_errors": (_int, [_vp, _vp, _int, _i32, _dbl, _dbl, _dbl, _dbl, _vp]),
     "b2rl_per_get_info": (_int, [_vp, ctypes.POINTER(PerInfo), _vp]),
     "b2rl_per_read_priorities": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "b2rl_per_set_max_priority": (_int, [_vp, _dbl, _vp]),
     "b2rl_replay_gather": (
         _int, [_vp, _vp, _i32, _vp, _int, ctypes.c_float, ctypes.POINTER(BatchOut), _vp]),
     "b2rl_c51_loss_fwd": (_int, [_vp] * 7 + [_i32, _i32, _int] + [_vp] * 5),

@@ -927,6 +927,22 @@ extern "C" int b2rl_per_get_info(b2rl_replay *h, b2rl_per_info *out, void *strea
     return B2RL_OK;
 }
 
+// Checkpoint restore: PrioritizedBuffer is pickled whole, max_priority included
+// (pfrl/replay_buffers/replay_buffer.py:85-94, collections/prioritized.py:32).
+extern "C" int b2rl_per_set_max_priority(b2rl_replay *h, double max_priority, void *stream)
+{
+    B2RL_REQUIRE(h, B2RL_ERR_INVALID, "null argument");
+    B2RL_REQUIRE(h->cfg.prioritized, B2RL_ERR_INVALID, "buffer has no priority trees");
+    B2RL_REQUIRE(max_priority > 0.0 && max_priority < INFINITY, B2RL_ERR_RANGE,
+                 "set_max_priority: value must be positive and finite");
+    cudaStream_t s = (cudaStream_t)stream;
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    B2RL_CUDA(cudaMemcpyAsync(&h->st->max_priority, &max_priority, sizeof(double),
+                              cudaMemcpyHostToDevice, s));
+    B2RL_CUDA(cudaStreamSynchronize(s)); // the source is a stack variable
+    return B2RL_OK;
+}
+
 extern "C" int b2rl_per_read_priorities(b2rl_replay *h, int64_t first, int64_t n, double *out,
                                         void *stream)
 {

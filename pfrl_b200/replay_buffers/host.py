@@ -57,5 +57,9 @@ class HostReplayBuffer:
             pickle.dump(list(self.memory), f)
 
     def load(self, filename):
-        with open(filename, "rb") as f:
-            self.memory = collections.deque(pickle.load(f), maxlen=self._capacity)
+        """Own format (a pickled list) or a checkpoint written by the
+        reference's ReplayBuffer.save (replay_buffer.py:85-94)."""
+        from pfrl_b200.replay_buffers import reference_pickle
+
+        items = reference_pickle.read(filename).experiences
+        self.memory = collections.deque(items, maxlen=self._capacity)

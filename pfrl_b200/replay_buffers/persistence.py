@@ -35,12 +35,7 @@ def save_buffer(buf, filename):
         np.savez(f, **meta, **arrays)
 
 
-def load_buffer(buf, filename):
-    with open(filename, "rb") as f:
-        z = np.load(f, allow_pickle=False)
-        z = {k: z[k] for k in z.files}
-    n = int(z["n"])
-    assert int(z["num_steps"]) == buf.num_steps
+def _reset(buf):
     if buf.store is not None:
         buf.store.close()
     buf.store = None
@@ -50,21 +45,80 @@ def load_buffer(buf, filename):
     buf._part_cache.clear()
     buf._live_min_seq.clear()
     buf.last_n_transitions.clear()
-    if n == 0:
-        return
-    pr = z.get("priority")
-    for k in range(n):
-        L = int(z["len"][k])
-        s, ns = z["state"][k], z["next_state"][k]
+    if buf._prioritized:
+        buf._waiting = False
+        buf._last_handle = None
+
+
+def _restore(buf, records, max_priority):
+    """Re-append ``records`` = iterable of (state, next_state, action,
+    step_rewards, terminal, priority-or-None), oldest first."""
+    _reset(buf)
+    for s, ns, action, rewards, term, priority in records:
         if buf.store is None:
-            buf._create_store(s, z["action"][k])
+            buf._create_store(s, action)
         s_slots, s_min = buf._parts_of(s)
         n_slots, n_min = buf._parts_of(ns)
-        act = buf.layout._action_array(z["action"][k]).tobytes()
-        buf._pend_exp.append((s_slots, n_slots, act, list(z["step_rewards"][k][:L]), L,
-                              bool(z["term"][k]), None if pr is None else float(pr[k])))
+        act = buf.layout._action_array(action).tobytes()
+        if buf._prioritized and priority is None:
+            raise ValueError("a prioritised buffer cannot be restored without priorities")
+        buf._pend_exp.append((s_slots, n_slots, act, [float(r) for r in rewards], len(rewards),
+                              bool(term), None if priority is None else float(priority)))
         buf._n_total += 1
         buf._live_min_seq.append(min(s_min, n_min))
+        if len(buf._live_min_seq) > buf._alloc_capacity:
+            buf._live_min_seq.popleft()
         if len(buf._pend_exp) >= 4096:
             buf._flush()
     buf._flush()
+    if buf._prioritized and buf.store is not None and max_priority is not None:
+        buf.store.set_max_priority(max_priority)
+
+
+def load_buffer(buf, filename):
+    from pfrl_b200.replay_buffers import reference_pickle
+
+    if reference_pickle.looks_like_pickle(filename):
+        return load_reference_pickle(buf, filename)
+    with open(filename, "rb") as f:
+        z = np.load(f, allow_pickle=False)
+        z = {k: z[k] for k in z.files}
+    n = int(z["n"])
+    assert int(z["num_steps"]) == buf.num_steps
+    pr = z.get("priority")
+
+    def records():
+        for k in range(n):
+            L = int(z["len"][k])
+            yield (z["state"][k], z["next_state"][k], z["action"][k], z["step_rewards"][k][:L],
+                   z["term"][k], None if pr is None else pr[k])
+
+    mp = z.get("max_priority")
+    _restore(buf, records(), None if mp is None else float(mp))
+
+
+def load_reference_pickle(buf, filename):
+    """Fill a device buffer from the reference's ``replay_buffer.pkl``
+    (pfrl/replay_buffers/replay_buffer.py:85-94, agents/dqn.py:794-810).  An
+    experience keeps what batch_experiences reads (replay_buffer.py:157-212):
+    state / action of its first transition, next_state of its last, the
+    per-step rewards and any(is_state_terminal)."""
+    from pfrl_b200.replay_buffers import reference_pickle
+
+    ref = reference_pickle.read(filename)
+    if buf._prioritized and ref.priorities is None:
+        raise TypeError("%s holds a uniform buffer; cannot load it into a prioritised one"
+                        % filename)
+    exps = ref.experiences
+    if any(len(e) > buf.num_steps for e in exps):
+        raise ValueError("checkpoint holds %d-step experiences, buffer was built with "
+                         "num_steps=%d" % (max(len(e) for e in exps), buf.num_steps))
+    pri = ref.priorities if buf._prioritized else None
+
+    def records():
+        for k, e in enumerate(exps):
+            yield (e[0]["state"], e[-1]["next_state"], e[0]["action"],
+                   [t["reward"] for t in e], any(t["is_state_terminal"] for t in e),
+                   None if pri is None else pri[k])
+
+    _restore(buf, records(), ref.max_priority if buf._prioritized else None)

@@ -163,6 +163,9 @@ class DeviceReplayStore:
         return dict(total=out.total, min=out.min, max_priority=out.max_priority,
                     napp=out.napp, npop=out.npop, scout_hits=out.scout_hits)
 
+    def set_max_priority(self, value):
+        _lib.check(self.L.b2rl_per_set_max_priority(self.h, float(value), _stream()))
+
     def read_priorities(self, first=0, n=None):
         if n is None:
             n = len(self) - first
