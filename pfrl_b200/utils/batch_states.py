@@ -30,6 +30,12 @@ def batch_states(states, device, phi):
         if mode == 0:
             return states
         return phi(states)
+    # host batch in one (possibly page-locked) slab: envs.MultiprocessVectorEnv
+    slab = getattr(states, "host_batch", None)
+    mode = getattr(phi, "b2rl_obs_mode", None)
+    if isinstance(slab, torch.Tensor) and mode in (0, 1) and torch.device(device).type == "cuda":
+        whole = slab.to(device)          # one copy for all environments (the slab is reused)
+        return whole.to(torch.float32) * phi.b2rl_obs_scale if mode == 1 else whole
     features = [phi(s) for s in states]
     collated = default_collate(features)
     if isinstance(features[0], tuple):
