@@ -455,7 +455,8 @@ class DeviceNStepBuffer:
 
     def _materialise(self, exps):
         out = self._gather(exps, 1.0, None, raw=True, want_steps=True)
-        torch.cuda.current_stream().synchronize()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
         st = out["state"].cpu().numpy()
         ns = out["next_state"].cpu().numpy()
         ac = out["action"].cpu().numpy()

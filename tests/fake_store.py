@@ -105,8 +105,16 @@ class OracleBackedStore(FakeStore):
         return (w, torch.tensor(probs, dtype=torch.float64)) if want_prob else w
 
     def update_priorities(self, priority):
-        self.tree.set_last_priority(np.asarray(priority, dtype=np.float64))
+        priority = np.asarray(priority, dtype=np.float64)
+        for i, p in zip(self._last_idx.tolist(), priority.tolist()):
+            self.records[i]["priority"] = p
+        self.tree.set_last_priority(priority)
+        self.max_priority = self.tree.max_priority
         self._last_idx = None
+
+    def read_priorities(self, first=0, n=None):
+        n = len(self.records) - first if n is None else n
+        return np.array([r["priority"] for r in self.records[first:first + n]], dtype=np.float64)
 
     def info(self):
         return dict(total=self.tree.total(), min=self.tree.min(),
