@@ -160,6 +160,7 @@ def main(out_dir):
     agent_losses(out_dir)
     normalizer(out_dir)
     a2c_trace(out_dir)
+    agent_traces(out_dir)
     g["numpy_version"] = np.array(np.__version__)
     np.savez_compressed(os.path.join(out_dir, "losses.npz"), **g)
     print("wrote losses.npz with", len(g), "arrays")
@@ -292,3 +293,92 @@ def a2c_trace(out_dir):
             g["%s_final_%s" % (kind, k)] = v.numpy().copy()
     np.savez_compressed(os.path.join(out_dir, "a2c_trace.npz"), **g)
     print("wrote a2c_trace.npz with", len(g), "arrays")
+
+
+def _make_trace_agent(lib, kind, rbuf):
+    """The same construction code serves the reference (lib = pfrl) and the
+    rebuild (lib = pfrl_b200) -- tests/test_agent_traces_cpu.py imports it."""
+    import torch
+
+    phi = lambda x: x.astype(np.float32, copy=False)  # noqa: E731
+    eps = lib.explorers.LinearDecayEpsilonGreedy(1.0, 0.1, 150, lambda: np.random.randint(2))
+    common = dict(replay_start_size=40, minibatch_size=16, update_interval=1,
+                  target_update_interval=20, phi=phi)
+    if kind == "ddqn":
+        q = lib.q_functions.FCStateQFunctionWithDiscreteAction(5, 2, 32, 2)
+        cls, explorer, kw = lib.agents.DoubleDQN, eps, {}
+    elif kind == "dqn_sum":
+        q = lib.q_functions.FCStateQFunctionWithDiscreteAction(5, 2, 32, 2)
+        cls, explorer = lib.agents.DQN, eps
+        kw = dict(clip_delta=False, batch_accumulator="sum", target_update_method="soft",
+                  soft_update_tau=0.05, max_grad_norm=1.0)
+    elif kind == "c51":
+        q = lib.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(
+            5, 2, 21, -1.0, 2.0, 32, 2)
+        cls, explorer, kw = lib.agents.CategoricalDQN, eps, {}
+    elif kind == "rainbow":
+        q = lib.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(
+            5, 2, 21, -1.0, 2.0, 32, 2)
+        lib.nn.to_factorized_noisy(q, sigma_scale=0.5)
+        cls, explorer, kw = lib.agents.CategoricalDoubleDQN, lib.explorers.Greedy(), {}
+    else:
+        raise ValueError(kind)
+    opt = torch.optim.Adam(q.parameters(), lr=1e-3, eps=1e-4)
+    return q, cls(q, opt, rbuf, 0.95, explorer, **common, **kw)
+
+
+def _run_trace(agent, rbuf, steps=260, n_envs=2, check=None):
+    from pfrl_b200.envs import ChainEnv
+
+    envs = [ChainEnv(seed=i) for i in range(n_envs)]
+    obs = [e.reset() for e in envs]
+    actions, stats = [], []
+    for t in range(steps):
+        a = [int(x) for x in agent.batch_act(obs)]
+        if check is not None:
+            check(t, a)
+        actions.append(a)
+        nobs, r, d, info = zip(*[e.step(x) for e, x in zip(envs, a)])
+        resets = [i["needs_reset"] for i in info]
+        agent.batch_observe(list(nobs), list(r), list(d), resets)
+        obs = [e.reset() if (dd or rr) else o for e, o, dd, rr in zip(envs, nobs, d, resets)]
+        st = dict(agent.get_statistics())
+        stats.append([st["average_q"], st["average_loss"], st["n_updates"], st["rlen"]])
+    return np.asarray(actions), np.asarray(stats, dtype=np.float64)
+
+
+TRACE_KINDS = ("ddqn", "dqn_sum", "c51", "rainbow")
+TRACE_PER = dict(alpha=0.6, beta0=0.4, betasteps=100, num_steps=3, normalize_by_max="memory")
+
+
+def agent_traces(out_dir):
+    """Seeded training runs of the reference's DQN family with 3-step prioritised
+    replay on two chain environments: chosen actions, statistics after every
+    vector step, final parameters and the final state of the priority trees.
+
+    One adapter sits at the documented dtype boundary (DESIGN.md section 1,
+    "dtype contract"): TD errors enter ``update_errors`` as Python floats.
+    Unadapted, numpy >= 2 keeps them np.float32 and the reference's tree then
+    sums in float32 -- a numpy-version artefact, not part of the algorithm."""
+    import torch
+
+    import pfrl
+
+    for kind in TRACE_KINDS:
+        rbuf = pfrl.replay_buffers.PrioritizedReplayBuffer(150, **TRACE_PER)
+        raw_update = rbuf.update_errors
+        rbuf.update_errors = lambda errors, raw=raw_update: raw([float(e) for e in errors])
+        torch.manual_seed(3)
+        q, agent = _make_trace_agent(pfrl, kind, rbuf)
+        g = {"init_" + k: v.numpy().copy() for k, v in q.state_dict().items()}
+        np.random.seed(9)
+        torch.manual_seed(9)
+        actions, stats = _run_trace(agent, rbuf)
+        g.update(actions=actions, stats=stats,
+                 total=np.float64(rbuf.memory.priority_sums.sum()),
+                 min=np.float64(rbuf.memory.priority_mins.min()),
+                 max_priority=np.float64(rbuf.memory.max_priority), beta=np.float64(rbuf.beta))
+        for k, v in q.state_dict().items():
+            g["final_" + k] = v.numpy().copy()
+        np.savez_compressed(os.path.join(out_dir, "agent_trace_%s.npz" % kind), **g)
+        print("wrote agent_trace_%s.npz:" % kind, int(stats[-1][2]), "updates")
