@@ -161,6 +161,7 @@ def main(out_dir):
     normalizer(out_dir)
     a2c_trace(out_dir)
     agent_traces(out_dir)
+    more_agent_traces(out_dir)
     g["numpy_version"] = np.array(np.__version__)
     np.savez_compressed(os.path.join(out_dir, "losses.npz"), **g)
     print("wrote losses.npz with", len(g), "arrays")
@@ -382,3 +383,134 @@ def agent_traces(out_dir):
             g["final_" + k] = v.numpy().copy()
         np.savez_compressed(os.path.join(out_dir, "agent_trace_%s.npz" % kind), **g)
         print("wrote agent_trace_%s.npz:" % kind, int(stats[-1][2]), "updates")
+
+
+# ---------------------------------------------------------------------------
+# IQN, SAC, TD3, DDPG (uniform replay) and PPO
+# ---------------------------------------------------------------------------
+MORE_TRACE_KINDS = ("iqn", "sac", "td3", "ddpg", "ppo")
+
+
+def _make_more_agent(lib, kind, rbuf):
+    import torch
+    from torch import distributions, nn
+
+    phi = lambda x: x.astype(np.float32, copy=False)  # noqa: E731
+    burn = lambda: np.random.uniform(-1, 1, size=1).astype(np.float32)  # noqa: E731
+
+    def qf():
+        return nn.Sequential(lib.nn.ConcatObsAndAction(), nn.Linear(6, 32), nn.ReLU(),
+                             nn.Linear(32, 1))
+
+    def det_policy():
+        return nn.Sequential(nn.Linear(5, 32), nn.ReLU(), nn.Linear(32, 1), nn.Tanh(),
+                             lib.policies.DeterministicHead())
+
+    adam = lambda m: torch.optim.Adam(m.parameters(), lr=3e-3)  # noqa: E731
+    if kind == "iqn":
+        from importlib import import_module
+
+        iqn = import_module(lib.__name__ + ".agents.iqn")
+        q = iqn.ImplicitQuantileQFunction(
+            psi=nn.Sequential(nn.Linear(5, 24), nn.ReLU()),
+            phi=nn.Sequential(iqn.CosineBasisLinear(8, 24), nn.ReLU()),
+            f=nn.Linear(24, 2))
+        eps = lib.explorers.LinearDecayEpsilonGreedy(1.0, 0.1, 150, lambda: np.random.randint(2))
+        return lib.agents.IQN(
+            q, adam(q), rbuf, 0.95, eps, replay_start_size=40, minibatch_size=16,
+            update_interval=1, target_update_interval=20, phi=phi,
+            quantile_thresholds_N=6, quantile_thresholds_N_prime=5, quantile_thresholds_K=4)
+    if kind == "sac":
+        def squashed(x):
+            mean, log_scale = torch.chunk(x, 2, dim=1)
+            base = distributions.Independent(
+                distributions.Normal(mean, torch.exp(torch.clamp(log_scale, -5, 2))), 1)
+            return distributions.transformed_distribution.TransformedDistribution(
+                base, [distributions.transforms.TanhTransform(cache_size=1)])
+
+        policy = nn.Sequential(nn.Linear(5, 32), nn.ReLU(), nn.Linear(32, 2),
+                               lib.nn.Lambda(squashed))
+        q1, q2 = qf(), qf()
+        return lib.agents.SoftActorCritic(
+            policy, q1, q2, adam(policy), adam(q1), adam(q2), rbuf, gamma=0.95,
+            replay_start_size=40, minibatch_size=16, entropy_target=-1.0,
+            temperature_optimizer_lr=3e-3, phi=phi, burnin_action_func=burn)
+    ex = lib.explorers.AdditiveGaussian(scale=0.3, low=-1, high=1)
+    if kind == "td3":
+        p, q1, q2 = det_policy(), qf(), qf()
+        return lib.agents.TD3(p, q1, q2, adam(p), adam(q1), adam(q2), rbuf, 0.95, ex,
+                              replay_start_size=40, minibatch_size=16, phi=phi,
+                              burnin_action_func=burn)
+    if kind == "ddpg":
+        p, q = det_policy(), qf()
+        return lib.agents.DDPG(p, q, adam(p), adam(q), rbuf, 0.95, ex, replay_start_size=40,
+                               minibatch_size=16, phi=phi, target_update_method="soft",
+                               target_update_interval=1, soft_update_tau=0.05,
+                               burnin_action_func=burn)
+    if kind == "ppo":
+        model = nn.Sequential(nn.Linear(5, 32), nn.Tanh(), lib.nn.Branched(
+            nn.Sequential(nn.Linear(32, 2), lib.policies.SoftmaxCategoricalHead()),
+            nn.Linear(32, 1)))
+        return lib.agents.PPO(
+            model, torch.optim.Adam(model.parameters(), lr=3e-3),
+            obs_normalizer=lib.nn.EmpiricalNormalization(5, clip_threshold=5), gamma=0.95,
+            lambd=0.9, phi=phi, update_interval=64, minibatch_size=16, epochs=3, clip_eps=0.2,
+            clip_eps_vf=0.3, entropy_coef=0.01, max_grad_norm=0.5)
+    raise ValueError(kind)
+
+
+def _module_attrs(agent):
+    import torch
+
+    return [(name, getattr(agent, name)) for name in agent.saved_attributes
+            if isinstance(getattr(agent, name, None), torch.nn.Module)]
+
+
+def _run_more_trace(agent, kind, steps, check=None):
+    from pfrl_b200.envs import ChainEnv
+
+    cont = kind in ("sac", "td3", "ddpg")
+    envs = [ChainEnv(continuous=cont, seed=i) for i in range(2)]
+    obs = [e.reset() for e in envs]
+    actions, stats = [], []
+    for t in range(steps):
+        a = np.asarray(agent.batch_act(obs))
+        if check is not None:
+            check(t, a)
+        actions.append(a.copy())
+        nobs, r, d, info = zip(*[e.step(x) for e, x in zip(envs, a)])
+        resets = [i["needs_reset"] for i in info]
+        agent.batch_observe(list(nobs), list(r), list(d), resets)
+        obs = [e.reset() if (dd or rr) else o for e, o, dd, rr in zip(envs, nobs, d, resets)]
+        stats.append([float(v) for _, v in agent.get_statistics()])
+    return np.asarray(actions), np.asarray(stats, dtype=np.float64)
+
+
+def more_agent_traces(out_dir):
+    """Seeded runs of the reference's IQN / SAC / TD3 / DDPG (uniform replay,
+    capacity wrap-around) and PPO on two chain environments."""
+    import random
+
+    import torch
+
+    import pfrl
+
+    for kind in MORE_TRACE_KINDS:
+        rbuf = None if kind == "ppo" else pfrl.replay_buffers.ReplayBuffer(150)
+        torch.manual_seed(3)
+        agent = _make_more_agent(pfrl, kind, rbuf)
+        g = {}
+        for name, mod in _module_attrs(agent):
+            for k, v in mod.state_dict().items():
+                g["init_%s__%s" % (name, k)] = v.numpy().copy()
+        np.random.seed(9)
+        torch.manual_seed(9)
+        random.seed(9)
+        actions, stats = _run_more_trace(agent, kind, 200 if kind == "ppo" else 160)
+        g.update(actions=actions, stats=stats,
+                 stat_names=np.array([n for n, _ in agent.get_statistics()]))
+        for name, mod in _module_attrs(agent):
+            for k, v in mod.state_dict().items():
+                g["final_%s__%s" % (name, k)] = v.numpy().copy()
+        np.savez_compressed(os.path.join(out_dir, "agent_trace_%s.npz" % kind), **g)
+        print("wrote agent_trace_%s.npz" % kind, dict(zip(g["stat_names"], stats[-1])))
