@@ -264,6 +264,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     print("numpy", np.__version__)
     gen_reference_checkpoints()
+    gen_state_dict_layouts()
     gen_per_trace("per_trace_1step", seed=11, capacity=300, num_steps=1, n_envs=1, steps=900,
                   batch=16, alpha=0.6, beta0=0.4, betasteps=200, normalize_by_max=True,
                   gamma=0.99)
@@ -286,3 +287,70 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def gen_state_dict_layouts():
+    """Parameter names and shapes of the reference's model classes (what its
+    <attr>.pt checkpoints contain), plus one real Rainbow checkpoint directory
+    written by the reference's Agent.save (agent.py:81-106)."""
+    import json
+
+    import torch
+    from torch import nn
+
+    import pfrl
+
+    def layout(m):
+        return {k: list(v.shape) for k, v in m.state_dict().items()}
+
+    torch.manual_seed(0)
+    noisy_ddqn = pfrl.q_functions.DistributionalDuelingDQN(18, 51, -10, 10)
+    pfrl.nn.to_factorized_noisy(noisy_ddqn, sigma_scale=0.5)
+    models = {
+        "LargeAtariCNN": pfrl.nn.LargeAtariCNN(),
+        "SmallAtariCNN": pfrl.nn.SmallAtariCNN(),
+        "MLP(7,3,(16,8))": pfrl.nn.MLP(7, 3, (16, 8)),
+        "EmpiricalNormalization(6)": pfrl.nn.EmpiricalNormalization(6),
+        "FCStateQFunctionWithDiscreteAction(5,3,16,2)":
+            pfrl.q_functions.FCStateQFunctionWithDiscreteAction(5, 3, 16, 2),
+        "DistributionalFCStateQFunctionWithDiscreteAction(5,3,11,-1,1,16,2)":
+            pfrl.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(5, 3, 11, -1, 1, 16, 2),
+        "DuelingDQN(6)": pfrl.q_functions.DuelingDQN(6),
+        "DistributionalDuelingDQN(18,51,-10,10)":
+            pfrl.q_functions.DistributionalDuelingDQN(18, 51, -10, 10),
+        "DistributionalDuelingDQN(18,51,-10,10)+noisy": noisy_ddqn,
+        "GaussianHeadWithStateIndependentCovariance(3,diagonal)":
+            pfrl.policies.GaussianHeadWithStateIndependentCovariance(3, var_type="diagonal"),
+        "Branched(Linear(4,2),Linear(4,1))": pfrl.nn.Branched(nn.Linear(4, 2), nn.Linear(4, 1)),
+    }
+    with open(os.path.join(OUT, "ref_state_dict_layouts.json"), "w") as f:
+        json.dump({k: layout(m) for k, m in models.items()}, f, indent=1, sort_keys=True)
+
+    # a real checkpoint: small Rainbow agent after a few updates
+    torch.manual_seed(1)
+    np.random.seed(1)
+    q = pfrl.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(5, 2, 11, -1, 2, 16, 2)
+    pfrl.nn.to_factorized_noisy(q, sigma_scale=0.5)
+    rbuf = pfrl.replay_buffers.PrioritizedReplayBuffer(100, num_steps=2)
+    agent = pfrl.agents.CategoricalDoubleDQN(
+        q, torch.optim.Adam(q.parameters(), lr=1e-3), rbuf, 0.9, pfrl.explorers.Greedy(),
+        replay_start_size=20, minibatch_size=8, target_update_interval=10,
+        phi=lambda x: x.astype(np.float32, copy=False))
+    rng = np.random.RandomState(2)
+    obs = [rng.randn(5).astype(np.float32)]
+    for t in range(60):
+        a = agent.batch_act(obs)
+        nobs = [rng.randn(5).astype(np.float32)]
+        done = t % 17 == 16
+        agent.batch_observe(nobs, [float(rng.randn())], [done], [False])
+        obs = nobs
+    ckpt = os.path.join(OUT, "ref_ckpt_rainbow")
+    agent.save(ckpt)
+    probe = rng.randn(4, 5).astype(np.float32)
+    torch.manual_seed(123)  # the noisy layers draw fresh noise at every forward
+    with torch.no_grad(), pfrl.utils.evaluating(agent.model):
+        out = agent.model(torch.tensor(probe))
+    np.savez_compressed(os.path.join(OUT, "ref_ckpt_rainbow_expected.npz"), probe=probe,
+                        q_values=out.q_values.numpy(), q_dist=out.q_dist.numpy(),
+                        optim_steps=np.int64(agent.optim_t))
+    print("wrote state-dict layouts and", sorted(os.listdir(ckpt)))
