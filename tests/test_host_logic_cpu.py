@@ -135,3 +135,44 @@ def test_vector_frame_stack_shares_frame_objects():
     obs3 = venv.reset(np.logical_not(d))
     assert all(f is obs3[2]._frames[0] for f in obs3[2]._frames)
     assert venv.num_envs == 3
+
+
+def test_explorers_consume_the_reference_stream():
+    """Every explorer against the real reference when it is present (build
+    container): same actions and same position of numpy's global stream."""
+    import pytest
+
+    from oracle import refimport
+
+    if not refimport.available():
+        pytest.skip("reference tree not present")
+    pfrl = refimport.import_reference()
+    from pfrl_b200 import action_value, explorers
+
+    q = torch.tensor([[0.3, -0.2, 1.1, 0.4]])
+    cases = [
+        ("ConstantEpsilonGreedy", (0.3, lambda: np.random.randint(4)), "discrete"),
+        ("LinearDecayEpsilonGreedy", (1.0, 0.1, 20, lambda: np.random.randint(4)), "discrete"),
+        ("ExponentialDecayEpsilonGreedy", (1.0, 0.05, 0.9, lambda: np.random.randint(4)), "discrete"),
+        ("Boltzmann", (0.7,), "discrete"),
+        ("Greedy", (), "discrete"),
+        ("AdditiveGaussian", (0.3, -1, 1), "continuous"),
+        ("AdditiveOU", (0.1, 0.2, 0.4), "continuous"),
+    ]
+    for name, args, kind in cases:
+        outs = []
+        for lib, av_cls in ((pfrl, pfrl.action_value.DiscreteActionValue),
+                            (explorers, action_value.DiscreteActionValue)):
+            ex = getattr(lib.explorers if lib is pfrl else lib, name)(*args)
+            np.random.seed(5)
+            acts = []
+            for t in range(40):
+                if kind == "discrete":
+                    a = ex.select_action(t, lambda: 2, action_value=av_cls(q))
+                else:
+                    a = ex.select_action(t, lambda: np.float32([0.2, -0.4]))
+                acts.append(np.asarray(a, dtype=np.float64))
+            outs.append((np.stack(acts), np.random.get_state()[1][:8].copy(), repr(ex)))
+        np.testing.assert_array_equal(outs[0][0], outs[1][0], err_msg=name)
+        assert np.array_equal(outs[0][1], outs[1][1]), name
+        assert outs[0][2] == outs[1][2], name
