@@ -2,3 +2,4 @@ from pfrl_b200.experiments.evaluator import Evaluator, eval_performance, save_ag
 from pfrl_b200.experiments.train_agent import train_agent  # NOQA
 from pfrl_b200.experiments.train_agent_batch import train_agent_batch  # NOQA
 from pfrl_b200.experiments.train_agent_batch import train_agent_batch_with_evaluation  # NOQA
+from pfrl_b200.experiments.hooks import LinearInterpolationHook, StepHook  # NOQA

@@ -176,3 +176,17 @@ def test_explorers_consume_the_reference_stream():
         np.testing.assert_array_equal(outs[0][0], outs[1][0], err_msg=name)
         assert np.array_equal(outs[0][1], outs[1][1]), name
         assert outs[0][2] == outs[1][2], name
+
+
+def test_linear_interpolation_hook():
+    """reference: tests/experiments_tests/test_hooks.py (values at the ends,
+    in between, and clamped outside [1, total_steps])."""
+    from pfrl_b200.experiments import LinearInterpolationHook, StepHook
+
+    seen = []
+    hook = LinearInterpolationHook(11, 1.0, 0.0, lambda env, agent, v: seen.append((env, agent, v)))
+    assert isinstance(hook, StepHook)
+    for step in (0, 1, 2, 6, 11, 50):
+        hook("env", "agent", step)
+    assert [s[:2] for s in seen] == [("env", "agent")] * 6
+    np.testing.assert_allclose([s[2] for s in seen], [1.0, 1.0, 0.9, 0.5, 0.0, 0.0], atol=1e-12)
