@@ -3,3 +3,6 @@ from pfrl_b200.experiments.train_agent import train_agent  # NOQA
 from pfrl_b200.experiments.train_agent_batch import train_agent_batch  # NOQA
 from pfrl_b200.experiments.train_agent_batch import train_agent_batch_with_evaluation  # NOQA
 from pfrl_b200.experiments.hooks import LinearInterpolationHook, StepHook  # NOQA
+from pfrl_b200.experiments.train_agent import train_agent_with_evaluation  # NOQA
+from pfrl_b200.experiments.evaluator import batch_run_evaluation_episodes  # NOQA
+from pfrl_b200.experiments.evaluator import run_evaluation_episodes  # NOQA

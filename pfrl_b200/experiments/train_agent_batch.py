@@ -103,9 +103,14 @@ def train_agent_batch_with_evaluation(
         agent, env, steps, eval_n_steps, eval_n_episodes, eval_interval, outdir,
         checkpoint_freq=None, max_episode_len=None, step_offset=0, eval_max_episode_len=None,
         return_window_size=100, eval_env=None, log_interval=None, successful_score=None,
-        step_hooks=(), save_best_so_far_agent=True, logger=None):
+        step_hooks=(), evaluation_hooks=(), save_best_so_far_agent=True, use_tensorboard=False,
+        logger=None):
     """train_agent_batch + periodic evaluation; returns (agent, history)."""
     logger = logger or logging.getLogger(__name__)
+    for hook in evaluation_hooks:
+        if not getattr(hook, "support_train_agent_batch", False):
+            raise ValueError(
+                "{} does not support train_agent_batch_with_evaluation().".format(hook))
     os.makedirs(outdir, exist_ok=True)
     if eval_env is None:
         eval_env = env
@@ -114,7 +119,8 @@ def train_agent_batch_with_evaluation(
     evaluator = Evaluator(
         agent=agent, n_steps=eval_n_steps, n_episodes=eval_n_episodes,
         eval_interval=eval_interval, outdir=outdir, max_episode_len=eval_max_episode_len,
-        env=eval_env, step_offset=step_offset, save_best_so_far_agent=save_best_so_far_agent,
+        env=eval_env, step_offset=step_offset, evaluation_hooks=evaluation_hooks,
+        save_best_so_far_agent=save_best_so_far_agent, use_tensorboard=use_tensorboard,
         logger=logger)
     history = train_agent_batch(
         agent, env, steps, outdir, checkpoint_freq=checkpoint_freq,
