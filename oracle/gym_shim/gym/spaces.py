@@ -24,6 +24,13 @@ class Box(Space):
             np.all(x >= self.low) and np.all(x <= self.high)
         )
 
+    def __eq__(self, other):
+        return (isinstance(other, Box) and self.shape == other.shape
+                and self.dtype == other.dtype and np.array_equal(self.low, other.low)
+                and np.array_equal(self.high, other.high))
+
+    __hash__ = None
+
 
 class Discrete(Space):
     def __init__(self, n):
@@ -36,3 +43,9 @@ class Discrete(Space):
 
     def contains(self, x):
         return 0 <= int(x) < self.n
+
+    def __eq__(self, other):
+        return isinstance(other, Discrete) and self.n == other.n
+
+    def __hash__(self):
+        return hash(("Discrete", self.n))

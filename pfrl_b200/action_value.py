@@ -118,6 +118,16 @@ class DistributionalDiscreteActionValue(ActionValue):
     def evaluate_actions_as_distribution(self, actions):
         return _row_gather(self.q_dist, actions)
 
+    # expectations-based helpers, as for plain Q-values
+    def compute_advantage(self, actions):
+        return self.evaluate_actions(actions) - self.max
+
+    def compute_double_advantage(self, actions, argmax_actions):
+        return self.evaluate_actions(actions) - self.evaluate_actions(argmax_actions)
+
+    def compute_expectation(self, beta):
+        return (torch.softmax(beta * self.q_values, dim=-1) * self.q_values).sum(dim=1)
+
     def __repr__(self):
         return "DistributionalDiscreteActionValue greedy_actions:{} q_values:{}".format(
             self.greedy_actions.detach().cpu().numpy(),
@@ -166,3 +176,47 @@ class QuantileDiscreteActionValue(DiscreteActionValue):
 
     def __getitem__(self, i):
         return QuantileDiscreteActionValue(self.quantiles[i], self.q_values_formatter)
+
+
+class SingleActionValue(ActionValue):
+    """Action value known only through callables: ``evaluator(actions)`` scores
+    given actions, ``maximizer()`` returns the greedy ones (continuous-action
+    critics; reference: pfrl/action_value.py:327-365).  Both results are computed
+    at most once."""
+
+    def __init__(self, evaluator, maximizer=None):
+        self.evaluator = evaluator
+        self.maximizer = maximizer
+        self._greedy = None
+        self._max = None
+
+    @property
+    def greedy_actions(self):
+        if self._greedy is None:
+            self._greedy = self.maximizer()
+        return self._greedy
+
+    @property
+    def max(self):
+        if self._max is None:
+            self._max = self.evaluator(self.greedy_actions)
+        return self._max
+
+    def evaluate_actions(self, actions):
+        return self.evaluator(actions)
+
+    def compute_advantage(self, actions):
+        return self.evaluator(actions) - self.max
+
+    def compute_double_advantage(self, actions, argmax_actions):
+        return self.evaluate_actions(actions) - self.evaluate_actions(argmax_actions)
+
+    def __repr__(self):
+        return "SingleActionValue"
+
+    @property
+    def params(self):
+        return ()
+
+    def __getitem__(self, i):
+        raise NotImplementedError

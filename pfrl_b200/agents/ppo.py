@@ -52,6 +52,9 @@ def _yield_minibatch_indices(order, minibatch_size, num_epochs):
         pool = pool[:-minibatch_size]
 
 
+_yield_minibatches = _yield_minibatch_indices  # the reference's name (works on any list)
+
+
 class PPO(agent.AttributeSavingMixin, agent.BatchAgent):
     saved_attributes = ("model", "optimizer", "obs_normalizer")
 

@@ -22,22 +22,7 @@ from pfrl_b200.utils import clip_l2_grad_norm_
 from pfrl_b200.utils.batch_states import batch_states
 from pfrl_b200.utils.modes import evaluating, no_distribution_validation
 from pfrl_b200.utils.copy_param import synchronize_parameters
-
-
-def mode_of_distribution(distrib):
-    """Most probable action (pfrl/utils/mode_of_distribution.py)."""
-    if isinstance(distrib, torch.distributions.Independent):
-        return mode_of_distribution(distrib.base_dist)
-    if isinstance(distrib, torch.distributions.Categorical):
-        return distrib.probs.argmax(dim=-1)
-    if isinstance(distrib, torch.distributions.Normal):
-        return distrib.mean
-    if isinstance(distrib, torch.distributions.TransformedDistribution):
-        x = mode_of_distribution(distrib.base_dist)
-        for transform in distrib.transforms:
-            x = transform(x)
-        return x
-    raise RuntimeError("{} is not supported".format(distrib))
+from pfrl_b200.utils.mode_of_distribution import mode_of_distribution  # NOQA (re-exported)
 
 
 class TemperatureHolder(nn.Module):

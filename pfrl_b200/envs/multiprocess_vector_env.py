@@ -21,6 +21,7 @@ Observations that are not fixed-shape arrays simply keep using the pipe.
 import mmap
 import multiprocessing
 import signal
+import traceback
 from multiprocessing import shared_memory
 
 import numpy as np
@@ -38,9 +39,17 @@ class HostObsList(list):
     host_batch = None
 
 
+_WORKER_ERROR = "__worker_error__"
+
+
 def _worker(remote, env_fn):
     signal.signal(signal.SIGINT, signal.SIG_IGN)  # the parent handles CTRL+C
-    environment = env_fn()
+    try:
+        environment = env_fn()
+    except BaseException:
+        remote.send((_WORKER_ERROR, traceback.format_exc()))
+        remote.close()
+        return
     shm = slab = row = None
 
     def ship(ob):
@@ -80,6 +89,10 @@ def _worker(remote, env_fn):
                 break
             else:
                 raise NotImplementedError(cmd)
+    except (EOFError, KeyboardInterrupt):
+        pass  # the parent went away
+    except BaseException:
+        remote.send((_WORKER_ERROR, traceback.format_exc()))
     finally:
         row = slab = None
         if shm is not None:
@@ -118,11 +131,24 @@ class MultiprocessVectorEnv(env.VectorEnv):
         self._row_fresh = [False] * len(env_fns)   # slab row i holds env i's current observation
         self._spec = None
         self.remotes[0].send(("get_spaces", None))
-        self.action_space, self.observation_space = self.remotes[0].recv()
+        self.action_space, self.observation_space = self._recv(0)
 
     def __del__(self):
         if not getattr(self, "closed", True):
             self.close()
+
+    def _recv(self, i):
+        """Answer of worker i; a worker that died or raised becomes a RuntimeError
+        here instead of a parent blocked on the pipe forever."""
+        remote = self.remotes[i]
+        while not remote.poll(0.5):
+            if not self.ps[i].is_alive() and not remote.poll(0):
+                raise RuntimeError("environment worker {} exited unexpectedly (exit code {})"
+                                   .format(i, self.ps[i].exitcode))
+        answer = remote.recv()
+        if isinstance(answer, tuple) and len(answer) == 2 and answer[0] == _WORKER_ERROR:
+            raise RuntimeError("environment worker {} failed:\n{}".format(i, answer[1]))
+        return answer
 
     # ------------------------------------------------------------------ slab
     def _maybe_create_slab(self, sample):
@@ -140,8 +166,8 @@ class MultiprocessVectorEnv(env.VectorEnv):
                 self._row_fresh[i] = True
         for i, remote in enumerate(self.remotes):
             remote.send(("attach", (self._shm.name, shape, sample.dtype.str, i)))
-        for remote in self.remotes:
-            assert remote.recv() is True
+        for i in range(self.num_envs):
+            assert self._recv(i) is True
         self._slab_tensor = torch.from_numpy(self._slab)
         if self._pin and torch.cuda.is_available():
             rc = torch.cuda.cudart().cudaHostRegister(self._slab_tensor.data_ptr(),
@@ -168,14 +194,14 @@ class MultiprocessVectorEnv(env.VectorEnv):
         if self._spec is None:
             self._assert_not_closed()
             self.remotes[0].send(("spec", None))
-            self._spec = self.remotes[0].recv()
+            self._spec = self._recv(0)
         return self._spec
 
     def step(self, actions):
         self._assert_not_closed()
         for remote, action in zip(self.remotes, actions):
             remote.send(("step", action))
-        results = [remote.recv() for remote in self.remotes]
+        results = [self._recv(i) for i in range(self.num_envs)]
         obs, rews, dones, infos = zip(*results)
         self.last_obs = [self._take(i, o) for i, o in enumerate(obs)]
         return self._wrap(self.last_obs), rews, dones, infos
@@ -187,9 +213,8 @@ class MultiprocessVectorEnv(env.VectorEnv):
         for keep, remote in zip(mask, self.remotes):
             if not keep:
                 remote.send(("reset", None))
-        self.last_obs = [o if keep else self._take(i, remote.recv())
-                         for i, (keep, remote, o) in enumerate(zip(mask, self.remotes,
-                                                                   self.last_obs))]
+        self.last_obs = [o if keep else self._take(i, self._recv(i))
+                         for i, (keep, o) in enumerate(zip(mask, self.last_obs))]
         first = next((o for o in self.last_obs if o is not None), None)
         self._maybe_create_slab(first)
         return self._wrap(self.last_obs)
@@ -208,15 +233,21 @@ class MultiprocessVectorEnv(env.VectorEnv):
             raise TypeError("Type of Seeds {} is not supported.".format(type(seeds)))
         for remote, seed in zip(self.remotes, seeds):
             remote.send(("seed", seed))
-        return [remote.recv() for remote in self.remotes]
+        return [self._recv(i) for i in range(self.num_envs)]
 
     def close(self):
         self._assert_not_closed()
         self.closed = True
-        for remote in self.remotes:
-            remote.send(("close", None))
+        for remote, p in zip(self.remotes, self.ps):
+            if p.is_alive():
+                try:
+                    remote.send(("close", None))
+                except (BrokenPipeError, OSError):
+                    pass
         for p in self.ps:
-            p.join()
+            p.join(timeout=10)
+            if p.is_alive():
+                p.terminate()
         if self._shm is not None:
             if self._pinned:
                 torch.cuda.cudart().cudaHostUnregister(self._slab_tensor.data_ptr())

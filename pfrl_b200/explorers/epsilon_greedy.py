@@ -19,40 +19,61 @@ def select_action_epsilon_greedily(epsilon, random_action_func, greedy_action_fu
     return greedy_action_func(), True
 
 
-class ConstantEpsilonGreedy(explorer.Explorer):
-    """Fixed epsilon (pfrl/explorers/epsilon_greedy.py:15-39)."""
+class _EpsilonGreedy(explorer.Explorer):
+    """Shared mechanics: with probability ``compute_epsilon(t)`` call
+    ``random_action_func()``, otherwise take the greedy action.  ``epsilon``
+    always holds the value used by the last decision."""
 
-    def __init__(self, epsilon, random_action_func, logger=getLogger(__name__)):
-        assert 0 <= epsilon <= 1
+    label = "EpsilonGreedy"
+
+    def __init__(self, epsilon, random_action_func, logger):
         self.epsilon = epsilon
         self.random_action_func = random_action_func
         self.logger = logger
 
+    def compute_epsilon(self, t):
+        return self.epsilon
+
     def select_action(self, t, greedy_action_func, action_value=None):
-        a, greedy = select_action_epsilon_greedily(
+        self.epsilon = self.compute_epsilon(t)
+        action, was_greedy = select_action_epsilon_greedily(
             self.epsilon, self.random_action_func, greedy_action_func)
-        self.logger.debug("t:%s a:%s %s", t, a, "greedy" if greedy else "non-greedy")
-        return a
+        self.logger.debug("t:%s a:%s %s", t, action, "greedy" if was_greedy else "non-greedy")
+        return action
 
     def __repr__(self):
-        return "ConstantEpsilonGreedy(epsilon={})".format(self.epsilon)
+        return "{}(epsilon={})".format(self.label, self.epsilon)
 
 
-class LinearDecayEpsilonGreedy(explorer.Explorer):
+def _check_probability(*values):
+    for v in values:
+        assert 0 <= v <= 1
+
+
+class ConstantEpsilonGreedy(_EpsilonGreedy):
+    """Fixed epsilon (pfrl/explorers/epsilon_greedy.py:15-39)."""
+
+    label = "ConstantEpsilonGreedy"
+
+    def __init__(self, epsilon, random_action_func, logger=getLogger(__name__)):
+        _check_probability(epsilon)
+        super().__init__(epsilon, random_action_func, logger)
+
+
+class LinearDecayEpsilonGreedy(_EpsilonGreedy):
     """Epsilon annealed linearly from start to end over decay_steps
     (pfrl/explorers/epsilon_greedy.py:42-88)."""
 
+    label = "LinearDecayEpsilonGreedy"
+
     def __init__(self, start_epsilon, end_epsilon, decay_steps, random_action_func,
                  logger=getLogger(__name__)):
-        assert 0 <= start_epsilon <= 1
-        assert 0 <= end_epsilon <= 1
+        _check_probability(start_epsilon, end_epsilon)
         assert decay_steps >= 0
+        super().__init__(start_epsilon, random_action_func, logger)
         self.start_epsilon = start_epsilon
         self.end_epsilon = end_epsilon
         self.decay_steps = decay_steps
-        self.random_action_func = random_action_func
-        self.logger = logger
-        self.epsilon = start_epsilon
 
     def compute_epsilon(self, t):
         if t > self.decay_steps:
@@ -60,15 +81,23 @@ class LinearDecayEpsilonGreedy(explorer.Explorer):
         span = self.end_epsilon - self.start_epsilon
         return self.start_epsilon + span * (t / self.decay_steps)
 
-    def select_action(self, t, greedy_action_func, action_value=None):
-        self.epsilon = self.compute_epsilon(t)
-        a, greedy = select_action_epsilon_greedily(
-            self.epsilon, self.random_action_func, greedy_action_func)
-        self.logger.debug("t:%s a:%s %s", t, a, "greedy" if greedy else "non-greedy")
-        return a
 
-    def __repr__(self):
-        return "LinearDecayEpsilonGreedy(epsilon={})".format(self.epsilon)
+class ExponentialDecayEpsilonGreedy(_EpsilonGreedy):
+    """epsilon_t = max(start * decay**t, end) (pfrl/explorers/epsilon_greedy.py:91-134)."""
+
+    label = "ExponentialDecayEpsilonGreedy"
+
+    def __init__(self, start_epsilon, end_epsilon, decay, random_action_func,
+                 logger=getLogger(__name__)):
+        _check_probability(start_epsilon, end_epsilon)
+        assert 0 < decay < 1
+        super().__init__(start_epsilon, random_action_func, logger)
+        self.start_epsilon = start_epsilon
+        self.end_epsilon = end_epsilon
+        self.decay = decay
+
+    def compute_epsilon(self, t):
+        return max(self.start_epsilon * (self.decay ** t), self.end_epsilon)
 
 
 class Greedy(explorer.Explorer):

@@ -1,5 +1,4 @@
-"""The reference's remaining explorers: exponentially decayed epsilon-greedy
-(pfrl/explorers/epsilon_greedy.py:91-134), Boltzmann sampling
+"""The reference's stochastic explorers: Boltzmann sampling
 (pfrl/explorers/boltzmann.py) and additive Ornstein-Uhlenbeck noise
 (pfrl/explorers/additive_ou.py).  Like the others they draw from numpy's
 global legacy stream in the reference's order, so seeded runs agree."""
@@ -9,36 +8,7 @@ import numpy as np
 import torch
 
 from pfrl_b200 import explorer
-from pfrl_b200.explorers.epsilon_greedy import select_action_epsilon_greedily
-
-
-class ExponentialDecayEpsilonGreedy(explorer.Explorer):
-    """epsilon_t = max(start * decay**t, end)."""
-
-    def __init__(self, start_epsilon, end_epsilon, decay, random_action_func,
-                 logger=getLogger(__name__)):
-        assert 0 <= start_epsilon <= 1
-        assert 0 <= end_epsilon <= 1
-        assert 0 < decay < 1
-        self.start_epsilon = start_epsilon
-        self.end_epsilon = end_epsilon
-        self.decay = decay
-        self.random_action_func = random_action_func
-        self.logger = logger
-        self.epsilon = start_epsilon
-
-    def compute_epsilon(self, t):
-        return max(self.start_epsilon * (self.decay ** t), self.end_epsilon)
-
-    def select_action(self, t, greedy_action_func, action_value=None):
-        self.epsilon = self.compute_epsilon(t)
-        a, greedy = select_action_epsilon_greedily(
-            self.epsilon, self.random_action_func, greedy_action_func)
-        self.logger.debug("t:%s a:%s %s", t, a, "greedy" if greedy else "non-greedy")
-        return a
-
-    def __repr__(self):
-        return "ExponentialDecayEpsilonGreedy(epsilon={})".format(self.epsilon)
+from pfrl_b200.explorers.epsilon_greedy import ExponentialDecayEpsilonGreedy  # NOQA (re-exported)
 
 
 class Boltzmann(explorer.Explorer):

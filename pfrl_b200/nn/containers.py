@@ -38,3 +38,25 @@ class ConcatObsAndAction(nn.Module):
         obs = obs.reshape(obs.shape + (1,) * (rank - obs.ndim))
         action = action.reshape(action.shape + (1,) * (rank - action.ndim))
         return torch.cat((obs, action), dim=-1)
+
+
+class BoundByTanh(nn.Module):
+    """Squash unbounded outputs into the action box: ``tanh(x) * (high - low) / 2
+    + (high + low) / 2`` (reference: pfrl/nn/bound_by_tanh.py, functions/
+    bound_by_tanh.py).  The bounds are converted once per device / dtype instead
+    of on every call; the module has no state_dict entries, like the reference's."""
+
+    def __init__(self, low, high):
+        super().__init__()
+        assert low is not None and high is not None
+        self.low, self.high = low, high
+        self._cache = None
+
+    def forward(self, x):
+        key = (x.device, x.dtype)
+        if self._cache is None or self._cache[0] != key:
+            low = torch.as_tensor(self.low, dtype=x.dtype, device=x.device)
+            high = torch.as_tensor(self.high, dtype=x.dtype, device=x.device)
+            self._cache = (key, (high - low) / 2, (high + low) / 2)
+        _, scale, loc = self._cache
+        return torch.tanh(x) * scale + loc

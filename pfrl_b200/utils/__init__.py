@@ -4,3 +4,5 @@ from pfrl_b200.utils.modes import evaluating  # NOQA
 from pfrl_b200.utils.copy_param import synchronize_parameters  # NOQA
 from pfrl_b200.utils.random import sample_n_k  # NOQA
 from pfrl_b200.utils.random_seed import set_random_seed  # NOQA
+from pfrl_b200.utils.mode_of_distribution import mode_of_distribution  # NOQA
+from pfrl_b200.utils import copy_param  # NOQA  (the module, as in the reference)

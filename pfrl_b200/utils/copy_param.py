@@ -28,6 +28,15 @@ def soft_copy_param(target_link, source_link, tau):
         torch._foreach_add_(f_t, f_s, alpha=tau)
 
 
+def copy_grad(target_link, source_link):
+    """Give ``target_link``'s parameters clones of ``source_link``'s gradients
+    (``None`` where the source has none)."""
+    pairs = zip(target_link.parameters(), source_link.parameters())
+    for dst, src in pairs:
+        assert dst.shape == src.shape
+        dst.grad = None if src.grad is None else src.grad.clone()
+
+
 def synchronize_parameters(src, dst, method, tau=None):
     """copy_param.py:37-41"""
     if method == "hard":

@@ -20,6 +20,12 @@ class VectorEnvWrapper(env.VectorEnv):
 
     def __init__(self, venv):
         self.env = venv
+        self.action_space = getattr(venv, "action_space", None)
+        self.observation_space = getattr(venv, "observation_space", None)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
 
     def __getattr__(self, name):
         if name.startswith("_"):
@@ -49,6 +55,9 @@ class VectorFrameStack(VectorEnvWrapper):
         self.k = k
         self.stack_axis = stack_axis
         self.frames = [deque([], maxlen=k) for _ in range(venv.num_envs)]
+        from pfrl_b200.wrappers.atari_wrappers import _stacked_space
+
+        self.observation_space = _stacked_space(self.observation_space, k, stack_axis)
 
     def _observations(self):
         assert all(len(f) == self.k for f in self.frames)

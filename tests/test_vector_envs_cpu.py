@@ -130,3 +130,24 @@ def test_ragged_observations_fall_back_to_the_pipe():
                 assert obss.host_batch is None
     finally:
         vec.close()
+
+
+def _broken_env():
+    raise ValueError("cannot build this env")
+
+
+class _FailsOnStep(WalkEnv):
+    def step(self, action):
+        raise KeyError("boom")
+
+
+def test_worker_failures_surface_in_the_parent():
+    with pytest.raises(RuntimeError, match="cannot build this env"):
+        MultiprocessVectorEnv([_broken_env])
+    vec = MultiprocessVectorEnv([WalkEnv, _FailsOnStep])
+    try:
+        vec.reset()
+        with pytest.raises(RuntimeError, match="boom"):
+            vec.step([0, 0])
+    finally:
+        vec.close()
