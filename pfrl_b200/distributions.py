@@ -1,53 +1,45 @@
-"""Extra torch.distributions used by deterministic policies."""
-from numbers import Number
+"""Degenerate distribution for deterministic policies (DDPG / TD3 heads).
+
+``DeterministicHead`` wraps the policy output in ``Independent(Delta(loc), 1)``
+so that agents can treat stochastic and deterministic policies alike:
+``sample()`` / ``rsample()`` return the location, ``mode_of_distribution`` its
+mean; a density does not exist, so ``log_prob`` and ``entropy`` refuse.
+(Reference counterpart: pfrl/distributions/delta.py.)
+"""
+import numbers
 
 import torch
 from torch.distributions import Distribution, constraints
 
 
-class Delta(Distribution):
-    """Point mass at ``loc`` (reference: pfrl/distributions/delta.py:7-62):
-    sampling returns ``loc`` (``rsample`` keeps the graph), density and entropy
-    are undefined."""
+def _no_density(*_args, **_kwargs):
+    raise RuntimeError("Not defined")
 
-    arg_constraints = {"loc": constraints.real}
-    support = constraints.real
+
+class Delta(Distribution):
     has_rsample = True
+    support = constraints.real
+    arg_constraints = {"loc": constraints.real}
 
     def __init__(self, loc, validate_args=None):
+        scalar = isinstance(loc, numbers.Number)
         self.loc = loc
-        shape = torch.Size() if isinstance(loc, Number) else self.loc.size()
-        super().__init__(shape, validate_args=validate_args)
+        super().__init__(torch.Size() if scalar else loc.size(), validate_args=validate_args)
 
-    @property
-    def mean(self):
-        return self.loc
-
-    @property
-    def stddev(self):
-        return torch.zeros_like(self.loc)
-
-    @property
-    def variance(self):
-        return torch.zeros_like(self.loc)
-
-    def expand(self, batch_shape, _instance=None):
-        new = self._get_checked_instance(Delta, _instance)
-        batch_shape = torch.Size(batch_shape)
-        new.loc = self.loc.expand(batch_shape)
-        super(Delta, new).__init__(batch_shape, validate_args=False)
-        new._validate_args = self._validate_args
-        return new
+    # moments: all mass at loc
+    mean = property(lambda self: self.loc)
+    stddev = property(lambda self: torch.zeros_like(self.loc))
+    variance = stddev
 
     def rsample(self, sample_shape=torch.Size()):
+        """The location itself (differentiable), broadcast to the sample shape."""
         return self.loc.expand(self._extended_shape(sample_shape))
 
     def sample(self, sample_shape=torch.Size()):
-        with torch.no_grad():
-            return self.rsample(sample_shape).detach()
+        return self.rsample(sample_shape).detach()
 
-    def log_prob(self, value):
-        raise RuntimeError("Not defined")
+    def expand(self, batch_shape, _instance=None):
+        return Delta(self.loc.expand(torch.Size(batch_shape)), validate_args=False)
 
-    def entropy(self):
-        raise RuntimeError("Not defined")
+    log_prob = _no_density
+    entropy = _no_density
