@@ -14,6 +14,7 @@ __version__ = "0.1.0"
 from pfrl_b200 import action_value  # NOQA
 from pfrl_b200 import agent  # NOQA
 from pfrl_b200 import agents  # NOQA
+from pfrl_b200 import collections  # NOQA
 from pfrl_b200 import distributions  # NOQA
 from pfrl_b200 import env  # NOQA
 from pfrl_b200 import envs  # NOQA

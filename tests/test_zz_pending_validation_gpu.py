@@ -100,3 +100,11 @@ def test_pinned_slab_uploads_in_one_copy():
         np.testing.assert_array_equal(b.cpu().numpy(), np.stack(obs))   # the first upload is a copy
     finally:
         vec.close()
+
+
+def test_collections_prioritized_buffer_on_cuda():
+    from test_collections_cpu import replay_collections_trace
+    from pfrl_b200.collections import PrioritizedBuffer
+
+    buf = replay_collections_trace(lambda cap: PrioritizedBuffer(capacity=cap))
+    assert len(buf) == 300

@@ -73,6 +73,7 @@ for name, mod in list(sys.modules.items()):
 
 from fake_store import OracleBackedStore
 mock.patch("pfrl_b200.replay_buffers.device_buffer.DeviceReplayStore", OracleBackedStore).start()
+mock.patch("pfrl_b200.collections.prioritized.DeviceReplayStore", OracleBackedStore).start()
 mock.patch("torch.cuda.current_device", return_value=0).start()
 
 def pytest_configure(config):
