@@ -6,7 +6,7 @@ pfrl/replay_buffers/replay_buffer.py:11-94 (n-step window per env_id, uniform
 import collections
 import pickle
 
-from pfrl_b200.utils.random import sample_n_k
+from pfrl_b200.collections.random_access_queue import RandomAccessQueue
 
 
 class HostReplayBuffer:
@@ -14,7 +14,7 @@ class HostReplayBuffer:
         assert num_steps > 0
         self._capacity = capacity
         self.num_steps = num_steps
-        self.memory = collections.deque(maxlen=capacity)
+        self.memory = RandomAccessQueue(maxlen=capacity)   # O(1) indexing for sample()
         self.last_n_transitions = collections.defaultdict(
             lambda: collections.deque([], maxlen=num_steps))
 
@@ -47,7 +47,7 @@ class HostReplayBuffer:
 
     def sample(self, num_experiences):
         assert len(self.memory) >= num_experiences
-        return [self.memory[int(i)] for i in sample_n_k(len(self.memory), num_experiences)]
+        return self.memory.sample(num_experiences)
 
     def __len__(self):
         return len(self.memory)
@@ -62,4 +62,4 @@ class HostReplayBuffer:
         from pfrl_b200.replay_buffers import reference_pickle
 
         items = reference_pickle.read(filename).experiences
-        self.memory = collections.deque(items, maxlen=self._capacity)
+        self.memory = RandomAccessQueue(items, maxlen=self._capacity)

@@ -34,7 +34,8 @@ DEFAULT = [
     "utils_tests/test_mode_of_distribution.py", "utils_tests/test_random.py",
     "utils_tests/test_random_seed.py", "wrappers_tests/test_vector_frame_stack.py",
     # envs_tests/test_vector_envs.py needs gym.make("CartPole-v0"): see tests/test_vector_envs_cpu.py
-    "replay_buffers_test/test_replay_buffer.py",
+    "replay_buffers_test/test_replay_buffer.py", "collections_tests/test_random_access_queue.py",
+    "collections_tests/test_prioritized.py",
     "agents_tests/test_dqn.py", "agents_tests/test_double_dqn.py",
     "agents_tests/test_categorical_dqn.py", "agents_tests/test_double_categorical_dqn.py",
     "agents_tests/test_iqn.py", "agents_tests/test_ppo.py", "agents_tests/test_a2c.py",
