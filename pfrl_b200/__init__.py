@@ -23,6 +23,7 @@ from pfrl_b200 import explorer  # NOQA
 from pfrl_b200 import explorers  # NOQA
 from pfrl_b200 import initializers  # NOQA
 from pfrl_b200 import nn  # NOQA
+from pfrl_b200 import optimizers  # NOQA
 from pfrl_b200 import policies  # NOQA
 from pfrl_b200 import q_function  # NOQA
 from pfrl_b200 import q_functions  # NOQA

@@ -7,3 +7,4 @@ from pfrl_b200.agents.iqn import IQN  # NOQA
 from pfrl_b200.agents.ppo import PPO  # NOQA
 from pfrl_b200.agents.soft_actor_critic import SoftActorCritic  # NOQA
 from pfrl_b200.agents.td3 import DDPG, TD3  # NOQA
+from pfrl_b200.agents import ddpg  # NOQA  (module path of the reference)
