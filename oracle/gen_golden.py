@@ -265,6 +265,7 @@ def main():
     print("numpy", np.__version__)
     gen_reference_checkpoints()
     gen_state_dict_layouts()
+    gen_seeded_init()
     gen_per_trace("per_trace_1step", seed=11, capacity=300, num_steps=1, n_envs=1, steps=900,
                   batch=16, alpha=0.6, beta0=0.4, betasteps=200, normalize_by_max=True,
                   gamma=0.99)
@@ -354,3 +355,33 @@ def gen_state_dict_layouts():
                         q_values=out.q_values.numpy(), q_dist=out.q_dist.numpy(),
                         optim_steps=np.int64(agent.optim_t))
     print("wrote state-dict layouts and", sorted(os.listdir(ckpt)))
+
+
+def gen_seeded_init():
+    """Initial parameters the reference's constructors produce under
+    torch.manual_seed(11) (same-seed reproducibility of a drop-in)."""
+    import torch
+
+    import pfrl
+
+    g = {}
+
+    def rec(name, make):
+        torch.manual_seed(11)
+        for k, v in make().state_dict().items():
+            g[name + "__" + k] = v.numpy().copy()
+
+    def noisy():
+        q = pfrl.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(
+            5, 2, 11, -1.0, 2.0, 16, 2)
+        pfrl.nn.to_factorized_noisy(q, sigma_scale=0.5)
+        return q
+
+    rec("FCQ", lambda: pfrl.q_functions.FCStateQFunctionWithDiscreteAction(5, 2, 32, 2))
+    rec("DistFCQ", lambda: pfrl.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(
+        5, 2, 21, -1.0, 2.0, 32, 2))
+    rec("MLP", lambda: pfrl.nn.MLP(7, 3, (16, 8)))
+    rec("SmallAtariCNN", lambda: pfrl.nn.SmallAtariCNN())
+    rec("NoisyDistFCQ", noisy)
+    np.savez_compressed(os.path.join(OUT, "ref_seeded_init.npz"), **g)
+    print("wrote ref_seeded_init.npz with", len(g), "arrays")

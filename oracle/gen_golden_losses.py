@@ -162,6 +162,7 @@ def main(out_dir):
     a2c_trace(out_dir)
     agent_traces(out_dir)
     more_agent_traces(out_dir)
+    driver_trace(out_dir)
     g["numpy_version"] = np.array(np.__version__)
     np.savez_compressed(os.path.join(out_dir, "losses.npz"), **g)
     print("wrote losses.npz with", len(g), "arrays")
@@ -514,3 +515,52 @@ def more_agent_traces(out_dir):
                 g["final_%s__%s" % (name, k)] = v.numpy().copy()
         np.savez_compressed(os.path.join(out_dir, "agent_trace_%s.npz" % kind), **g)
         print("wrote agent_trace_%s.npz" % kind, dict(zip(g["stat_names"], stats[-1])))
+
+
+def _run_driver(lib, rbuf, outdir):
+    """train_agent_batch_with_evaluation on two chain envs + a separate eval
+    vector env: the whole loop (per-env step counting, resets, evaluator
+    schedule, scores.txt) in one seeded run.  Shared by both sides."""
+    import logging
+
+    import torch
+
+    from pfrl_b200.envs import ChainEnv
+
+    torch.manual_seed(3)
+    q, agent = _make_trace_agent(lib, "ddqn", rbuf)
+    np.random.seed(9)
+    torch.manual_seed(9)
+    env = lib.envs.SerialVectorEnv([ChainEnv(seed=i) for i in range(2)])
+    eval_env = lib.envs.SerialVectorEnv([ChainEnv(seed=10 + i) for i in range(3)])
+    log = logging.getLogger("b2rl.driver_trace")
+    log.setLevel(logging.CRITICAL)
+    agent2, history = lib.experiments.train_agent_batch_with_evaluation(
+        agent=agent, env=env, steps=700, eval_n_steps=None, eval_n_episodes=4, eval_interval=150,
+        outdir=outdir, eval_env=eval_env, max_episode_len=25, log_interval=None, logger=log)
+    rows = [ln.split("\t") for ln in open(os.path.join(outdir, "scores.txt")).read().strip()
+            .splitlines()]
+    return q, agent, history, rows
+
+
+def driver_trace(out_dir):
+    import tempfile
+
+    import pfrl
+
+    rbuf = pfrl.replay_buffers.PrioritizedReplayBuffer(150, **TRACE_PER)
+    raw_update = rbuf.update_errors
+    rbuf.update_errors = lambda errors: raw_update([float(e) for e in errors])
+    with tempfile.TemporaryDirectory() as d:
+        q, agent, history, rows = _run_driver(pfrl, rbuf, d)
+        saved = sorted(os.listdir(d))
+    header, body = rows[0], rows[1:]
+    keep = [i for i, name in enumerate(header) if name != "elapsed"]
+    g = dict(header=np.array([header[i] for i in keep]),
+             scores=np.array([[float(r[i]) for i in keep] for r in body], dtype=np.float64),
+             eval_scores=np.array([h["eval_score"] for h in history], dtype=np.float64),
+             saved=np.array(saved), t=np.int64(agent.t), optim_t=np.int64(agent.optim_t))
+    for k, v in q.state_dict().items():
+        g["final_" + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(out_dir, "driver_trace.npz"), **g)
+    print("wrote driver_trace.npz:", len(body), "evaluations, saved", saved)

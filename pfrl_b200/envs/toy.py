@@ -16,6 +16,10 @@ class ChainEnv:
         self.n_actions = 2
         self.obs_dim = size
         self.act_dim = 1
+        # vector-env wrappers (ours and the reference's) read these from their first env
+        self.action_space = None
+        self.observation_space = None
+        self.spec = None
 
     def _obs(self):
         o = np.zeros(self.size, dtype=np.float32)

@@ -18,14 +18,17 @@ class MLP(nn.Module):
         self.in_size, self.out_size = in_size, out_size
         self.hidden_sizes = hidden_sizes
         self.nonlinearity = nonlinearity
-        fan_in = in_size
+        widths = [in_size] + list(hidden_sizes)
         if hidden_sizes:
-            layers = []
-            for width in hidden_sizes:
-                layers.append(init_chainer_default(nn.Linear(fan_in, width)))
-                fan_in = width
-            self.hidden_layers = nn.ModuleList(layers)
-        self.output = nn.Linear(fan_in, out_size)
+            # all hidden Linear layers are constructed (torch's default init draws from
+            # the global generator) BEFORE any of them is re-initialised, and the output
+            # layer after that: the reference's order, so that the same torch seed gives
+            # the same initial weights (tests/test_checkpoint_interchange_cpu.py)
+            self.hidden_layers = nn.ModuleList(
+                [nn.Linear(a, b) for a, b in zip(widths, widths[1:])])
+            for layer in self.hidden_layers:
+                init_chainer_default(layer)
+        self.output = nn.Linear(widths[-1], out_size)
         init_lecun_normal(self.output.weight, scale=last_wscale)
         nn.init.zeros_(self.output.bias)
 

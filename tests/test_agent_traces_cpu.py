@@ -110,3 +110,29 @@ def test_more_agents_reproduce_the_reference_run(kind):
             # measured: bit-equal for IQN, <= 4e-7 absolute for the others
             np.testing.assert_allclose(v.numpy(), g["final_%s__%s" % (name, k)], rtol=1e-5,
                                        atol=2e-6, err_msg="%s.%s" % (name, k))
+
+
+def test_whole_training_driver_reproduces_the_reference_run(tmp_path):
+    """train_agent_batch_with_evaluation end to end (vector-env loop, per-env step
+    counting, max_episode_len resets, evaluator schedule and episode accounting,
+    scores.txt, saved directories) against the reference's seeded run
+    (tests/golden/driver_trace.npz)."""
+    import pfrl_b200
+    from oracle.gen_golden_losses import _run_driver
+    from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
+
+    g = np.load(os.path.join(GOLD, "driver_trace.npz"))
+    with mock.patch("pfrl_b200.replay_buffers.device_buffer.DeviceReplayStore", OracleBackedStore):
+        rbuf = PrioritizedReplayBuffer(150, device=0, **TRACE_PER)
+        q, agent, history, rows = _run_driver(pfrl_b200, rbuf, str(tmp_path))
+    header, body = rows[0], rows[1:]
+    keep = [i for i, name in enumerate(header) if name != "elapsed"]
+    assert [header[i] for i in keep] == g["header"].tolist()
+    got = np.array([[float(r[i]) for i in keep] for r in body], dtype=np.float64)
+    assert got.shape == g["scores"].shape
+    np.testing.assert_allclose(got, g["scores"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose([h["eval_score"] for h in history], g["eval_scores"], rtol=1e-12)
+    assert sorted(os.listdir(str(tmp_path))) == g["saved"].tolist()
+    assert agent.t == int(g["t"]) and agent.optim_t == int(g["optim_t"])
+    for k, v in q.state_dict().items():
+        np.testing.assert_allclose(v.numpy(), g["final_" + k], rtol=1e-5, atol=1e-6, err_msg=k)

@@ -73,3 +73,30 @@ def test_reference_agent_checkpoint_loads_and_reproduces_outputs():
     # target net differs from the online net (it was last synchronised some updates ago)
     assert any(not torch.equal(a, b) for a, b in zip(agent.model.parameters(),
                                                      agent.target_model.parameters()))
+
+
+def test_same_torch_seed_gives_the_reference_initial_weights():
+    """Constructors consume torch's global generator in the reference's order
+    (tests/golden/ref_seeded_init.npz, oracle/gen_golden.py:gen_seeded_init), so a
+    script that only sets the seed starts from the same network."""
+    import pfrl_b200 as lib
+
+    g = np.load(os.path.join(GOLD, "ref_seeded_init.npz"))
+
+    def noisy():
+        q = lib.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(5, 2, 11, -1.0, 2.0, 16, 2)
+        lib.nn.to_factorized_noisy(q, sigma_scale=0.5)
+        return q
+
+    makers = {
+        "FCQ": lambda: lib.q_functions.FCStateQFunctionWithDiscreteAction(5, 2, 32, 2),
+        "DistFCQ": lambda: lib.q_functions.DistributionalFCStateQFunctionWithDiscreteAction(
+            5, 2, 21, -1.0, 2.0, 32, 2),
+        "MLP": lambda: lib.nn.MLP(7, 3, (16, 8)),
+        "SmallAtariCNN": lambda: lib.nn.SmallAtariCNN(),
+        "NoisyDistFCQ": noisy,
+    }
+    for name, make in makers.items():
+        torch.manual_seed(11)
+        for k, v in make().state_dict().items():
+            np.testing.assert_array_equal(v.numpy(), g[name + "__" + k], err_msg=name + "." + k)
