@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: long-running test")
+    config.addinivalue_line("markers", "timeout(seconds): per-test limit (pytest-timeout)")
 
 
 def _has_cuda():

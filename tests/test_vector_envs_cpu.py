@@ -7,6 +7,9 @@ import pytest
 
 from pfrl_b200.envs import MultiprocessVectorEnv, SerialVectorEnv
 
+# subprocess tests: a stuck worker must fail the test, not hang the run
+pytestmark = pytest.mark.timeout(180)
+
 
 class WalkEnv:
     action_space = "Discrete(3)"
