@@ -63,6 +63,9 @@ def parse():
                     help="CPU baseline budget (timed part)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rainbow", action="store_true")
+    ap.add_argument("--rainbow-graph", action="store_true",
+                    help="replay the Rainbow learn step as one CUDA graph (N = 1 only; off by "
+                         "default: not part of the measured round-1 configuration)")
     return ap.parse_args()
 
 
@@ -185,7 +188,7 @@ RAINBOW_ENVS = 16
 RAINBOW_UPDATE_INTERVAL = 4
 
 
-def make_rainbow_agent(buf, dev_index, batch, grad_sync=None):
+def make_rainbow_agent(buf, dev_index, batch, grad_sync=None, cuda_graph=False):
     import torch
     from pfrl_b200 import agents, explorers, nn as pnn, parallel, q_functions
     from pfrl_b200.utils.phi import ScaleU8
@@ -199,7 +202,7 @@ def make_rainbow_agent(buf, dev_index, batch, grad_sync=None):
         q, opt, buf, gpu=dev_index, gamma=GAMMA, explorer=explorers.Greedy(),
         minibatch_size=batch, replay_start_size=batch, target_update_interval=32000,
         update_interval=RAINBOW_UPDATE_INTERVAL, batch_accumulator="mean", phi=ScaleU8(),
-        grad_sync=grad_sync)
+        grad_sync=grad_sync, cuda_graph=cuda_graph)
     parallel.broadcast_parameters(agent.model)
     parallel.broadcast_parameters(agent.target_model)
     return agent
@@ -501,7 +504,8 @@ def main():
         torch.backends.cudnn.allow_tf32 = False  # fp32 parity configuration
         torch.backends.cuda.matmul.allow_tf32 = False
         agent = make_rainbow_agent(buf, local_rank, B,
-                                   grad_sync=parallel.GradSync() if world > 1 else None)
+                                   grad_sync=parallel.GradSync() if world > 1 else None,
+                                   cuda_graph=args.rainbow_graph and world == 1)
         vec_steps = max(8, min(K, 40))
         res = {}
         for tag, env_dev in (("value", dev), ("e2e", "cpu")):
