@@ -197,7 +197,15 @@ __device__ __forceinline__ void st_tree(double *ptr, double v, uint64_t pol)
                  : "memory");
 }
 
-template <int R>
+// FMA (experimental, opt-in with B2RL_SAMPLER_DESCENT=fma until validated on a GPU): the
+// conditional subtraction `if (right) x -= left` becomes ONE fused multiply-add with a
+// lane-constant multiplier instead of a subtraction plus a 64-bit select (2 x FSEL) and
+// the predicate traffic around it.  fma(-1, left, x) rounds x - left once, exactly like
+// __dsub_rn; fma(-0, left, x) = x + (-0) = x because tree values are finite and >= 0.
+// The arithmetic of the winning lane is therefore bit for bit the reference's.  Static
+// SASS count of k_sample_exact_deep<8>: 1448 -> 1304 instructions (FSEL 114 -> 0,
+// ISETP 100 -> 52), i.e. ~14 % of the issue-bound per-draw body.
+template <int R, bool FMA>
 __device__ __forceinline__ void spec_round(const double *val, int &node, double &pos, int lane)
 {
     static_assert(R >= 1 && R <= 5, "one round covers at most 5 levels");
@@ -215,7 +223,11 @@ __device__ __forceinline__ void spec_round(const double *val, int &node, double 
         const bool right = (li >> (R - 1 - j)) & 1;
         const bool lt = x < left[j];
         ok = ok && (lt != right);
-        if (right) x = __dsub_rn(x, left[j]);
+        if constexpr (FMA) {
+            x = __fma_rn(right ? -1.0 : -0.0, left[j], x);
+        } else {
+            if (right) x = __dsub_rn(x, left[j]);
+        }
     }
     unsigned m = __ballot_sync(0xffffffffu, ok);
     if constexpr (R < 5) m &= (1u << (1 << R)) - 1u;
@@ -224,13 +236,13 @@ __device__ __forceinline__ void spec_round(const double *val, int &node, double 
     node = (node << R) + win;
 }
 
-template <int L>
+template <int L, bool FMA = false>
 __device__ __forceinline__ void spec_descend(const double *val, int &node, double &pos, int lane)
 {
     if constexpr (L > 0) {
         constexpr int R = L >= 5 ? 5 : L;
-        spec_round<R>(val, node, pos, lane);
-        spec_descend<L - R>(val, node, pos, lane);
+        spec_round<R, FMA>(val, node, pos, lane);
+        spec_descend<L - R, FMA>(val, node, pos, lane);
     }
 }
 
@@ -313,7 +325,7 @@ __device__ __forceinline__ void st_release_smem(int *p, int v)
 // stay bit-identical to the reference.
 // Shared memory: [top 2^14 f64][sub_own 2^(D+1)][sub_pref 2 x 2^(D+1)][out
 // staging][flags][mbarrier].  The top arrives / leaves by bulk async copy.
-template <int D>
+template <int D, bool FMA>
 __global__ void __launch_bounds__(96, 1) k_sample_exact_deep(SampleArgs a)
 {
     constexpr int T = TOP_LEVELS; // shared memory holds heap levels 0..T-1
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(96, 1) k_sample_exact_deep(SampleArgs a)
                         node = older ^ 1;
                     }
                 }
-                spec_descend<T - 2>(top, node, pos, lane); // level 1 -> T-1
+                spec_descend<T - 2, FMA>(top, node, pos, lane); // level 1 -> T-1
                 const unsigned unode = (unsigned)node;
                 // ---- the D levels under `node`: staged by the scout, or fetched here
                 const double *sub;
@@ -450,7 +462,7 @@ __global__ void __launch_bounds__(96, 1) k_sample_exact_deep(SampleArgs a)
                     sub = sub_own;
                 }
                 int rel = 1;
-                spec_descend<D>(sub, rel, pos, lane);
+                spec_descend<D, FMA>(sub, rel, pos, lane);
                 const unsigned leafnode = (unode << D) + (unsigned)(rel - (1 << D));
                 const double prio = sub[rel];
                 // ---- re-reduce the path: siblings first, then the add chain ---
@@ -516,21 +528,38 @@ __global__ void __launch_bounds__(96, 1) k_sample_exact_deep(SampleArgs a)
     }
 }
 
-template <int D>
-static cudaError_t launch_deep(const SampleArgs &a, cudaStream_t s)
+template <int D, bool FMA>
+static cudaError_t launch_deep_as(const SampleArgs &a, cudaStream_t s)
 {
     const size_t smem = sizeof(double) * ((size_t(1) << TOP_LEVELS) + 4 * (size_t(2) << D) + 32) +
                         sizeof(int) * (32 + 16) + 16;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_sample_exact_deep<D>,
+        cudaError_t e = cudaFuncSetAttribute(k_sample_exact_deep<D, FMA>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_sample_exact_deep<D><<<1, 96, smem, s>>>(a);
+    k_sample_exact_deep<D, FMA><<<1, 96, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+static bool fma_descent_requested()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("B2RL_SAMPLER_DESCENT");
+        cached = (e && e[0] == 'f') ? 1 : 0;
+    }
+    return cached == 1;
+}
+
+template <int D>
+static cudaError_t launch_deep(const SampleArgs &a, cudaStream_t s)
+{
+    return fma_descent_requested() ? launch_deep_as<D, true>(a, s)
+                                   : launch_deep_as<D, false>(a, s);
 }
 
 static cudaError_t launch_exact_deep(const SampleArgs &a, cudaStream_t s)
