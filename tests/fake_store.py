@@ -81,11 +81,16 @@ class OracleBackedStore(FakeStore):
 
     def append(self, state_parts, next_parts, action, rewards, length, terminal, priority=None):
         n = np.asarray(state_parts).reshape(-1, self.stack).shape[0]
+        if self.tree is not None:
+            # a restored max_priority (set_max_priority) lives here; the oracle tree only
+            # learns its max through set_last_priority
+            self.max_priority = max(self.max_priority, self.tree.max_priority)
         super().append(state_parts, next_parts, action, rewards, length, terminal, priority)
         self.napp += n
         if self.tree is not None:
             for i in range(n):
-                self.tree.append(None, None if priority is None else float(priority[i]))
+                self.tree.append(None, self.max_priority if priority is None
+                                 else float(priority[i]))
 
     def sample(self, u, mode=0, want_index=True, want_priority=True):
         assert mode == 0, "the oracle restates the exact (sequential) sampler only"
@@ -118,7 +123,7 @@ class OracleBackedStore(FakeStore):
 
     def info(self):
         return dict(total=self.tree.total(), min=self.tree.min(),
-                    max_priority=self.tree.max_priority, napp=self.napp,
+                    max_priority=max(self.tree.max_priority, self.max_priority), napp=self.napp,
                     npop=self.napp - len(self.records), scout_hits=0)
 
     def gather(self, n, gamma_pow, index=None, obs_mode=0, obs_scale=1.0, obs_dtype=None,

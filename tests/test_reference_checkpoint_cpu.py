@@ -100,7 +100,13 @@ def test_device_buffers_restore_reference_checkpoints():
         # LazyFrames de-duplication: far fewer parts than 2 * 4 frames per experience
         assert store.part_head < 2.2 * int(exp["n"])
         # appending afterwards continues the same ring
-        per.append(np.zeros((4, 6, 6), np.uint8), 1, 0.5, np.ones((4, 6, 6), np.uint8))
+        from pfrl_b200.utils.lazy_frames import LazyFrames
+
+        frames = [np.full((1, 6, 6), i, np.uint8) for i in range(5)]
+        per.append(LazyFrames(frames[:4], stack_axis=0), 1, 0.5,
+                   LazyFrames(frames[1:], stack_axis=0))
+        per._flush()
+        assert store.records[-1]["priority"] == float(exp["max_priority"])
 
         exp = _expected("ref_uniform_3step")
         uni = ReplayBuffer(capacity=50, num_steps=3, device=0)

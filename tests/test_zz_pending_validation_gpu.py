@@ -43,7 +43,10 @@ def test_reference_pickle_into_cuda_store():
     assert np.array_equal(b["discount"].cpu().numpy(), exp["discount"])
     assert np.array_equal(b["is_state_terminal"].cpu().numpy(), exp["is_state_terminal"])
     # a new transition is appended with the restored max_priority
-    per.append(np.zeros((4, 6, 6), np.uint8), 1, 0.5, np.ones((4, 6, 6), np.uint8))
+    from pfrl_b200.utils.lazy_frames import LazyFrames
+
+    frames = [np.full((1, 6, 6), i, np.uint8) for i in range(5)]
+    per.append(LazyFrames(frames[:4], stack_axis=0), 1, 0.5, LazyFrames(frames[1:], stack_axis=0))
     per._flush()
     assert per.store.read_priorities()[-1] == float(exp["max_priority"])
 
