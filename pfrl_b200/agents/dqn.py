@@ -353,6 +353,12 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
         return None
 
     # ------------------------------------------------------------------- misc
+    def stop_episode(self):
+        """Nothing to forget between episodes without recurrent state (dqn.py:791-793)."""
+
+    def update_from_episodes(self, episodes, errors_out=None):
+        raise NotImplementedError("episodic (recurrent) updates are out of scope of pfrl_b200")
+
     def save_snapshot(self, dirname):
         self.save(dirname)
         torch.save(self.t, "{}/t.pt".format(dirname))

@@ -527,6 +527,19 @@ class PriorityWeightError(object):
             out.append((d + eps) ** alpha)
         return out
 
+    def weights_from_probabilities(self, probabilities, min_probability):
+        """Host form of the importance weights (replay_buffers/prioritized.py:57-66),
+        for code that calls it directly; ``sample()`` computes the same numbers on the
+        device (k_weights).  Advances the beta schedule like the reference."""
+        if self.normalize_by_max == "batch":
+            min_probability = np.min(probabilities)
+        if self.normalize_by_max:
+            weights = [(p / min_probability) ** -self.beta for p in probabilities]
+        else:
+            weights = [(len(self) * p) ** -self.beta for p in probabilities]
+        self.beta = min(1.0, self.beta + self.beta_add)
+        return weights
+
 
 class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
     """Proportional prioritised replay (pfrl/replay_buffers/prioritized.py:

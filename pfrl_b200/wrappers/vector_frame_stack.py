@@ -18,10 +18,10 @@ from pfrl_b200.utils.lazy_frames import LazyFrames
 class VectorEnvWrapper(env.VectorEnv):
     """Forwards everything to the wrapped vector env."""
 
-    def __init__(self, venv):
-        self.env = venv
-        self.action_space = getattr(venv, "action_space", None)
-        self.observation_space = getattr(venv, "observation_space", None)
+    def __init__(self, env):
+        self.env = env
+        self.action_space = getattr(env, "action_space", None)
+        self.observation_space = getattr(env, "observation_space", None)
 
     @property
     def unwrapped(self):
@@ -36,25 +36,36 @@ class VectorEnvWrapper(env.VectorEnv):
     def num_envs(self):
         return self.env.num_envs
 
-    def step(self, actions):
-        return self.env.step(actions)
+    def step(self, action):
+        return self.env.step(action)
 
     def reset(self, mask=None):
         return self.env.reset(mask)
 
-    def seed(self, seeds):
-        return self.env.seed(seeds)
+    def seed(self, seed=None):
+        return self.env.seed(seed)
+
+    def render(self, mode="human", **kwargs):
+        return self.env.render(mode, **kwargs)
+
+    def compute_reward(self, achieved_goal, desired_goal, info):
+        return self.env.compute_reward(achieved_goal, desired_goal, info)
 
     def close(self):
         return self.env.close()
 
+    def __str__(self):
+        return "<{}{}>".format(type(self).__name__, self.env)
+
+    __repr__ = __str__
+
 
 class VectorFrameStack(VectorEnvWrapper):
-    def __init__(self, venv, k, stack_axis=0):
-        super().__init__(venv)
+    def __init__(self, env, k, stack_axis=0):
+        super().__init__(env)
         self.k = k
         self.stack_axis = stack_axis
-        self.frames = [deque([], maxlen=k) for _ in range(venv.num_envs)]
+        self.frames = [deque([], maxlen=k) for _ in range(env.num_envs)]
         from pfrl_b200.wrappers.atari_wrappers import _stacked_space
 
         self.observation_space = _stacked_space(self.observation_space, k, stack_axis)
@@ -72,8 +83,8 @@ class VectorFrameStack(VectorEnvWrapper):
                 frames.extend([ob] * self.k)
         return self._observations()
 
-    def step(self, actions):
-        batch_ob, rewards, dones, infos = self.env.step(actions)
+    def step(self, action):
+        batch_ob, rewards, dones, infos = self.env.step(action)
         for frames, ob in zip(self.frames, batch_ob):
             frames.append(ob)
         return self._observations(), rewards, dones, infos
