@@ -10,7 +10,7 @@ class LazyFrames(object):
     attribute and de-duplicate frames by identity.
     """
 
-    def __init__(self, frames, stack_axis=0):
+    def __init__(self, frames, stack_axis=2):  # the reference's default (hwc frames)
         self.stack_axis = stack_axis
         self._frames = frames
 
