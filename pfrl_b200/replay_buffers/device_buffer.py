@@ -39,6 +39,13 @@ class _Layout:
     def __init__(self, state, action):
         frames = getattr(state, "_frames", None)
         if frames is not None:
+            if getattr(state, "stack_axis", 0) != 0:
+                # parts are laid out back to back in the gathered observation, which is a
+                # concatenation along the FIRST axis (chw frames); hwc stacks interleave
+                raise TypeError(
+                    "device replay buffers need LazyFrames stacked along axis 0 (channel-first "
+                    "frames, e.g. VectorFrameStack(stack_axis=0) / FrameStack(channel_order="
+                    "'chw')); got stack_axis=%r" % (state.stack_axis,))
             first = frames[0]
             self.lazy = True
             self.stack = len(frames)

@@ -121,3 +121,14 @@ def test_device_buffers_restore_reference_checkpoints():
         one = ReplayBuffer(capacity=50, num_steps=1, device=0)
         with pytest.raises(ValueError):
             one.load(os.path.join(GOLD, "ref_uniform_3step.pkl"))
+
+
+def test_hwc_lazy_frames_are_refused_loudly():
+    from pfrl_b200.replay_buffers import ReplayBuffer
+    from pfrl_b200.utils.lazy_frames import LazyFrames
+
+    frames = [np.zeros((6, 6, 1), np.uint8) for _ in range(5)]
+    with mock.patch("pfrl_b200.replay_buffers.device_buffer.DeviceReplayStore", FakeStore):
+        buf = ReplayBuffer(10, device=0)
+        with pytest.raises(TypeError, match="stack_axis"):
+            buf.append(LazyFrames(frames[:4]), 0, 0.0, LazyFrames(frames[1:]))   # default axis 2
