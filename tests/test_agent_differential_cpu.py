@@ -1,4 +1,4 @@
-"""Randomised differential test of PPO against the REAL reference (build
+"""Randomised differential tests of PPO, A2C and the DQN family against the REAL reference (build
 container only): scripted random observations / rewards with random `done`
 and `reset` patterns over several environments, so that episode segmentation,
 the flush of unfinished episodes at update time, the dataset order that fixes
@@ -107,5 +107,62 @@ def test_a2c_random_done_patterns(seed):
     (a_ref, s_ref, p_ref), (a_me, s_me, p_me) = results
     assert np.array_equal(a_ref, a_me)
     np.testing.assert_allclose(s_me, s_ref, rtol=5e-5, atol=1e-6)
+    for x, y in zip(p_ref, p_me):
+        np.testing.assert_allclose(y, x, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["ddqn", "rainbow", "c51"])
+def test_dqn_family_random_done_reset_patterns(kind):
+    """DoubleDQN / Rainbow / C51 + 3-step prioritised replay (device buffer over the
+    host store emulation) on scripted random transitions of three environments with
+    random terminals AND random non-terminal resets."""
+    import os
+    import sys
+    from unittest import mock
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from fake_store import OracleBackedStore
+    from oracle.gen_golden_losses import TRACE_PER, _make_trace_agent
+
+    pfrl = refimport.import_reference()
+    import pfrl_b200
+
+    n_envs, T = 3, 120
+    rng = np.random.RandomState(len(kind))
+    obs = rng.randn(T + 1, n_envs, 5).astype(np.float32)
+    rew = rng.randn(T, n_envs)
+    done = rng.rand(T, n_envs) < 0.1
+    reset = (rng.rand(T, n_envs) < 0.07) & ~done
+    results = []
+    with mock.patch("pfrl_b200.replay_buffers.device_buffer.DeviceReplayStore", OracleBackedStore):
+        for lib in (pfrl, pfrl_b200):
+            if lib is pfrl:
+                rbuf = pfrl.replay_buffers.PrioritizedReplayBuffer(100, **TRACE_PER)
+                raw = rbuf.update_errors
+                rbuf.update_errors = lambda e, raw=raw: raw([float(x) for x in e])
+            else:
+                rbuf = pfrl_b200.replay_buffers.PrioritizedReplayBuffer(100, device=0, **TRACE_PER)
+            torch.manual_seed(5)
+            q, agent = _make_trace_agent(lib, kind, rbuf)
+            np.random.seed(6)
+            torch.manual_seed(6)
+            cur = [obs[0, i] for i in range(n_envs)]
+            acts, stats = [], []
+            for t in range(T):
+                a = [int(x) for x in agent.batch_act(cur)]
+                acts.append(a)
+                agent.batch_observe([obs[t + 1, i] for i in range(n_envs)], list(rew[t]),
+                                    list(done[t]), list(reset[t]))
+                cur = [obs[t + 1, i] * (-1.0 if (done[t, i] or reset[t, i]) else 1.0)
+                       for i in range(n_envs)]
+                st = dict(agent.get_statistics())
+                stats.append([st["average_q"], st["average_loss"], st["n_updates"], st["rlen"]])
+            results.append((acts, np.asarray(stats, dtype=np.float64),
+                            [p.detach().numpy().copy() for p in q.parameters()]))
+    (a_ref, s_ref, p_ref), (a_me, s_me, p_me) = results
+    assert a_ref == a_me
+    assert np.array_equal(s_ref[:, 2:], s_me[:, 2:])
+    live = s_ref[:, 2] > 0
+    np.testing.assert_allclose(s_me[live, :2], s_ref[live, :2], rtol=5e-5, atol=1e-6)
     for x, y in zip(p_ref, p_me):
         np.testing.assert_allclose(y, x, rtol=1e-5, atol=2e-6)
