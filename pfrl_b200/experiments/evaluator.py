@@ -70,6 +70,13 @@ def run_evaluation_episodes(env, agent, n_steps, n_episodes, max_episode_len=Non
 
 
 # ------------------------------------------------------------------ vector env
+def _on_host(values, dtype):
+    """Rewards / dones of a vector env as a numpy array (device envs may hand out tensors)."""
+    if hasattr(values, "detach"):
+        values = values.detach().cpu().numpy()
+    return np.asarray(values, dtype=dtype)
+
+
 class _StartOrderLedger(object):
     """Episodes of a vector env, identified by the order in which they start."""
 
@@ -99,7 +106,8 @@ def _batch_run_episodes(env, agent, n_steps, n_episodes, max_episode_len, logger
     obss = env.reset()
     while True:
         obss, rs, dones, infos = env.step(agent.batch_act(obss))
-        ret += rs
+        ret += _on_host(rs, np.float64)
+        dones = _on_host(dones, bool)
         length += 1
         resets = np.zeros(num_envs, dtype=bool) if max_episode_len is None \
             else length == max_episode_len
