@@ -166,3 +166,54 @@ def test_dqn_family_random_done_reset_patterns(kind):
     np.testing.assert_allclose(s_me[live, :2], s_ref[live, :2], rtol=5e-5, atol=1e-6)
     for x, y in zip(p_ref, p_me):
         np.testing.assert_allclose(y, x, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["sac", "td3", "ddpg", "iqn"])
+def test_uniform_replay_agents_random_done_reset_patterns(kind):
+    """SAC / TD3 / DDPG / IQN on the uniform device buffer (host store emulation) with
+    scripted random transitions, random terminals and random non-terminal resets."""
+    import os
+    import sys
+    from unittest import mock
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    from fake_store import OracleBackedStore
+    from oracle.gen_golden_losses import _make_more_agent, _module_attrs
+
+    pfrl = refimport.import_reference()
+    import pfrl_b200
+
+    n_envs, T = 2, 110
+    rng = np.random.RandomState(len(kind) + 40)
+    obs = rng.randn(T + 1, n_envs, 5).astype(np.float32)
+    rew = rng.randn(T, n_envs)
+    done = rng.rand(T, n_envs) < 0.1
+    reset = (rng.rand(T, n_envs) < 0.07) & ~done
+    results = []
+    with mock.patch("pfrl_b200.replay_buffers.device_buffer.DeviceReplayStore", OracleBackedStore):
+        for lib in (pfrl, pfrl_b200):
+            rbuf = lib.replay_buffers.ReplayBuffer(90) if lib is pfrl else \
+                lib.replay_buffers.ReplayBuffer(90, device=0)
+            torch.manual_seed(21)
+            agent = _make_more_agent(lib, kind, rbuf)
+            np.random.seed(22)
+            torch.manual_seed(22)
+            cur = [obs[0, i] for i in range(n_envs)]
+            acts, stats = [], []
+            for t in range(T):
+                acts.append(np.asarray(agent.batch_act(cur), dtype=np.float64).copy())
+                agent.batch_observe([obs[t + 1, i] for i in range(n_envs)], list(rew[t]),
+                                    list(done[t]), list(reset[t]))
+                cur = [obs[t + 1, i] * (-1.0 if (done[t, i] or reset[t, i]) else 1.0)
+                       for i in range(n_envs)]
+                stats.append([float(v) for _, v in agent.get_statistics()])
+            params = [p.detach().numpy().copy() for _, m in _module_attrs(agent)
+                      for p in m.parameters()]
+            results.append((np.asarray(acts), np.asarray(stats), params))
+    (a_ref, s_ref, p_ref), (a_me, s_me, p_me) = results
+    np.testing.assert_allclose(a_me, a_ref, rtol=1e-5, atol=2e-6)
+    both_nan = np.isnan(s_ref) & np.isnan(s_me)
+    np.testing.assert_allclose(np.where(both_nan, 0, s_me), np.where(both_nan, 0, s_ref),
+                               rtol=5e-5, atol=2e-6)
+    for x, y in zip(p_ref, p_me):
+        np.testing.assert_allclose(y, x, rtol=1e-5, atol=2e-6)
