@@ -1,10 +1,7 @@
-"""GPU checks for code that landed after the round-1 GPU budget was spent
-(DESIGN.md section 9, item 5).  Everything here is already covered on the CPU
-through tests/fake_store.py; these variants run the same assertions against
-the CUDA store.  They are skipped unless B2RL_PENDING=1 so that an unvalidated
-test cannot mask the validated suite; the first GPU call of the next round is
-
-    B2RL_PENDING=1 python -m pytest tests/test_zz_pending_validation_gpu.py -x -q
+"""GPU variants of the CPU tests (tests/fake_store.py) for the reference-pickle
+restore into the CUDA store, collections.PrioritizedBuffer over the
+device trees (a1-a3), the pinned observation slab of MultiprocessVectorEnv (8f2)
+and A2C on a CUDA device (8f4).  First run on a B200 in round 2 (4 passed).
 """
 import os
 
@@ -12,11 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [
-    pytest.mark.gpu,
-    pytest.mark.skipif(os.environ.get("B2RL_PENDING") != "1",
-                       reason="pending first GPU validation: run with B2RL_PENDING=1"),
-]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
