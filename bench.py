@@ -1,24 +1,34 @@
 #!/usr/bin/env python
-"""bench.py -- the hot path's headline measurement (see DESIGN.md section d).
+"""bench.py -- the hot path's headline measurement.
 
 Workload (BASELINE.json configs[2], the configuration the metric is quoted
 on): Rainbow's replay path -- PrioritizedReplayBuffer(10**6, alpha=.5,
 beta0=.4, num_steps=3, normalize_by_max="memory") holding synthetic Atari
 transitions (84x84 uint8 frames, stack 4, frame-shared), minibatch 512.
-One "step" = one pass of the replay hot path over one minibatch:
+One replay PASS = one pass of the hot path over one minibatch:
 
-    prioritized sample(512) -> IS weights -> gather state/next_state as f32
-    (/255) + reward/discount/terminal/action -> TD-error -> priority write-back
+    priority write-back of the previous minibatch's TD errors -> prioritized
+    sample(512) -> IS weights -> gather state/next_state as f32 (/255) +
+    reward / discount / terminal / action            (ONE launch: k_replay_step)
 
-metric   replay_samples_per_sec (whole job, all ranks)
-value    device-resident: u / TD errors already in HBM resp. pinned, C-ABI calls
+One bench STEP = `--passes` (default 128) passes, so that the driver's
+`--steps 20` times >= 2 500 passes (>= 1 s) and one host hiccup cannot move
+the number.
+
+metric   replay_samples_per_sec (whole job, all ranks), EXACT sampler
+         (bit-identical indices to the reference)
+value    device-resident: uniforms and TD errors already in HBM, C-ABI calls
 e2e      public API with HOST buffers: buf.sample() -> batch_experiences() ->
          D2H of weights/reward/indices -> buf.update_errors(host float list)
-roofline the gather kernel (dominant in bytes), CUDA events inside the timed
-         region, vs MEASURED_PEAKS.json hbm_gbs
-cpu_baseline / --impl reference: oracle/pyport.py (pure-Python port with the
-         reference's cost profile; the reference itself cannot travel to the
-         GPU box), single thread, bounded sample of the same workload.
+roofline the PATH: SURVEY 8(d) algorithmic bytes per sample x samples per
+         pass / pass time, vs MEASURED_PEAKS.json hbm_gbs; per-kernel
+         sub-records from the stand-alone kernels
+throughput_mode  the same pass with the PARALLEL sampler (all descents
+         concurrent on the frozen tree, with replacement), its own roofline
+secondary  BASELINE configs[1] (DQN B=32), [3] (PPO), [4] (SAC) lines
+cpu_baseline / --impl reference: the reference's OWN classes on the host
+         (oracle/_ref archive of pfnet/pfrl, kind "reference"; the pure-Python
+         port oracle/pyport.py only if the archive is absent), bounded sample.
 
 Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under
 torch.distributed.run (one rank per GPU, NCCL only for the timing barrier and
@@ -44,28 +54,31 @@ GAMMA = 0.99
 ALPHA = 0.5
 BETA0 = 0.4
 FRAME_BYTES = 84 * 84
-# algorithmic bytes per sampled experience, f32 outputs (DESIGN.md section d):
+# Algorithmic bytes per sampled experience, f32 outputs:
 # 7 distinct input frames (3-step, stack 4) + state and next_state as f32
 # + scalars (action 8, reward 4, terminal 4, discount 4, weight 4, index 8)
 ALGO_BYTES_GATHER = 7 * FRAME_BYTES + 2 * STACK * FRAME_BYTES * 4 + 32
+# ... + tree traffic of the draw and of the write-back (~1.7 KB) = 276.9 KB
+ALGO_BYTES_TREE = 1684
+ALGO_BYTES_PATH = ALGO_BYTES_GATHER + ALGO_BYTES_TREE
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--passes", type=int, default=128, help="replay passes per bench step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--capacity", type=int, default=10 ** 6)
     ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--mode", default="exact", choices=["exact", "parallel"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0,
                     help="CPU baseline budget (timed part)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rainbow", action="store_true")
-    ap.add_argument("--rainbow-graph", action="store_true",
-                    help="replay the Rainbow learn step as one CUDA graph (N = 1 only; off by "
-                         "default: not part of the measured round-1 configuration)")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-rainbow-graph", action="store_true",
+                    help="run the Rainbow learn step eagerly instead of as one CUDA graph")
     return ap.parse_args()
 
 
@@ -125,25 +138,21 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU baseline: pure-Python port of the reference path (oracle/pyport.py)
+# CPU arms (reference itself when oracle/_ref travelled, else the port)
 # ---------------------------------------------------------------------------
-def cpu_reference_run(capacity, batch, steps, warmup, seconds=None, pool=65536, seed=0):
-    """Time `steps` passes (or as many as fit in `seconds`) of
-    sample(batch) + batch_experiences + update_errors on the host."""
+def cpu_port_replay(capacity, batch, steps, warmup, seconds=None, pool=65536, seed=0):
+    """Fallback: pure-Python port of the reference path (oracle/pyport.py)."""
     import torch
     from oracle.pyport import PyPrioritizedReplayBuffer, py_batch_experiences
     from pfrl_b200.utils.lazy_frames import LazyFrames
 
-    torch.set_num_threads(min(16, os.cpu_count() or 1))  # collate only; the replay code is 1 thread
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
     rng = np.random.RandomState(seed)
     pool = min(pool, capacity + STACK + N_STEP)
     frames = rng.randint(0, 256, size=(pool, 1) + FRAME, dtype=np.uint8)
     flist = [frames[i] for i in range(pool)]
-    t0 = time.perf_counter()
     buf = PyPrioritizedReplayBuffer(capacity, alpha=ALPHA, beta0=BETA0, betasteps=None,
                                     num_steps=N_STEP, normalize_by_max="memory")
-    # setup (untimed): transitions share dicts between overlapping windows,
-    # observations share frames, exactly like the reference's storage
     T = capacity + N_STEP - 1
     obs = [LazyFrames([flist[(t + j) % pool] for j in range(STACK)], stack_axis=0)
            for t in range(T + 1)]
@@ -152,19 +161,16 @@ def cpu_reference_run(capacity, batch, steps, warmup, seconds=None, pool=65536, 
     trans = [dict(state=obs[t], action=int(acts[t]), reward=float(rews[t]),
                   next_state=obs[t + 1], next_action=None, is_state_terminal=False)
              for t in range(T)]
-    values = [trans[s:s + N_STEP] for s in range(capacity)]
-    buf.memory.bulk_load(values, rng.rand(capacity) + 0.05)
-    setup_s = time.perf_counter() - t0
+    buf.memory.bulk_load([trans[s:s + N_STEP] for s in range(capacity)],
+                         rng.rand(capacity) + 0.05)
     phi = lambda x: np.asarray(x, dtype=np.float32) / 255  # noqa: E731
     dev = torch.device("cpu")
     np.random.seed(seed)
 
     def one():
         exps = buf.sample(batch)
-        b = py_batch_experiences(exps, dev, phi, GAMMA)
-        err = [float(x) for x in np.abs(rng.randn(batch))]
-        buf.update_errors(err)
-        return b
+        py_batch_experiences(exps, dev, phi, GAMMA)
+        buf.update_errors([float(x) for x in np.abs(rng.randn(batch))])
 
     for _ in range(warmup):
         one()
@@ -177,7 +183,38 @@ def cpu_reference_run(capacity, batch, steps, warmup, seconds=None, pool=65536, 
             break
     dt = time.perf_counter() - t0
     return {"samples_per_sec": done * batch / dt, "steps": done, "seconds": dt,
-            "ms_per_step": 1e3 * dt / done, "setup_s": setup_s, "pool": pool}
+            "ms_per_step": 1e3 * dt / done, "kind": "port", "cores": 1}
+
+
+def cpu_arm(capacity, batch, steps, warmup, seconds, rainbow_seconds):
+    """(replay result, rainbow result or None) from the reference itself when it is
+    importable (oracle/_ref archive or /root/reference), else from the port."""
+    from oracle import ref_bench
+
+    if ref_bench.kind() == "reference":
+        r = ref_bench.replay_run(capacity, batch, steps, warmup, seconds=seconds, n_step=N_STEP,
+                                 alpha=ALPHA, beta0=BETA0, normalize_by_max="memory", gamma=GAMMA)
+        rb = None
+        if rainbow_seconds:
+            rb = ref_bench.rainbow_run(r["buffer"], r["frames"], batch, rainbow_seconds,
+                                       num_envs=RAINBOW_ENVS,
+                                       update_interval=RAINBOW_UPDATE_INTERVAL, gamma=GAMMA)
+        r.pop("buffer", None)
+        r.pop("frames", None)
+        return r, rb
+    r = cpu_port_replay(capacity, batch, steps, warmup, seconds=seconds)
+    rb = None
+    if rainbow_seconds:
+        rb = cpu_port_rainbow(capacity, batch, rainbow_seconds)
+    return r, rb
+
+
+def cpu_sample_text(r, batch):
+    what = ("the reference's own PrioritizedReplayBuffer.sample + batch_experiences + "
+            "update_errors (pfnet/pfrl, oracle/_ref)" if r["kind"] == "reference" else
+            "pure-Python port of the reference (oracle/pyport.py)")
+    return ("%d passes (%.1f s) of sample(%d)+batch_experiences+update_errors, 1M-leaf tree, "
+            "LazyFrames over a pool of 65536 frames; %s" % (r["steps"], r["seconds"], batch, what))
 
 
 # ---------------------------------------------------------------------------
@@ -219,9 +256,6 @@ def rainbow_loop(agent, env, vec_steps):
 
 
 def best_torch_threads():
-    """Pick the intra-op thread count that makes the CPU baseline FASTEST
-    (all cores oversubscribes badly on shared 100+-core hosts): probe a
-    Rainbow-sized forward/backward at a few counts and keep the best."""
     import torch
     from oracle.pyport_rainbow import RainbowNet
 
@@ -242,8 +276,8 @@ def best_torch_threads():
     return best
 
 
-def cpu_rainbow_run(capacity, batch, seconds, num_envs=RAINBOW_ENVS, pool=65536, seed=0):
-    """CPU port of the same loop: pyport replay + plain-torch Rainbow update."""
+def cpu_port_rainbow(capacity, batch, seconds, num_envs=RAINBOW_ENVS, pool=65536, seed=0):
+    """Fallback CPU port of the Rainbow loop: pyport replay + plain-torch update."""
     import torch
     from oracle.pyport import PyPrioritizedReplayBuffer
     from oracle.pyport_rainbow import PyRainbow
@@ -291,7 +325,7 @@ def cpu_rainbow_run(capacity, batch, seconds, num_envs=RAINBOW_ENVS, pool=65536,
     dt = time.perf_counter() - t0
     return {"env_steps_per_sec": env_steps / dt, "updates_per_sec": updates / dt,
             "ms_per_update": 1e3 * dt / max(updates, 1), "seconds": dt, "num_envs": num_envs,
-            "threads": torch.get_num_threads()}
+            "threads": torch.get_num_threads(), "kind": "port"}
 
 
 # ---------------------------------------------------------------------------
@@ -304,19 +338,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(args.capacity, args.batch, args.steps, args.warmup)
-        rb = None if args.no_rainbow else cpu_rainbow_run(args.capacity, args.batch, 20.0)
+        # each step = a bounded sample of the same workload: ONE pass (0.1-0.2 s of host
+        # work), not `--passes` of them, so that K steps end within minutes
+        r, rb = cpu_arm(args.capacity, args.batch, args.steps, args.warmup, None,
+                        None if args.no_rainbow else 20.0)
         line = {
             "impl": "reference", "metric": "replay_samples_per_sec", "value": r["samples_per_sec"],
             "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64 priorities / u8->f32 frames", "data": "synthetic",
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": r["samples_per_sec"], "unit": "samples/s", "cores": 1,
-                             "kind": "port",
-                             "sample": "%d steps of sample(%d)+batch_experiences+update_errors, "
-                                       "1M-leaf tree, frames from a pool of %d"
-                                       % (r["steps"], args.batch, r["pool"])},
+            "config": workload_config(args, 1, passes=1),
+            "cpu_baseline": {"value": r["samples_per_sec"], "unit": "samples/s",
+                             "cores": r["cores"], "kind": r["kind"],
+                             "sample": cpu_sample_text(r, args.batch)},
             "e2e": {"value": r["samples_per_sec"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
         }
@@ -325,7 +359,7 @@ def main():
                                "e2e_env_steps_per_sec": rb["env_steps_per_sec"],
                                "updates_per_sec": rb["updates_per_sec"],
                                "ms_per_update": rb["ms_per_update"], "num_envs": rb["num_envs"],
-                               "torch_threads": rb["threads"], "kind": "port",
+                               "torch_threads": rb["threads"], "kind": rb["kind"],
                                "sample": "%.0f s of act/append/sample(%d)/update on the host"
                                          % (rb["seconds"], args.batch)}
         print(json.dumps(line))
@@ -339,17 +373,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    import ctypes
+
     from pfrl_b200 import _lib
     from pfrl_b200.replay_buffer import batch_experiences
     from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
     from pfrl_b200.utils.phi import ScaleU8
 
     B, cap = args.batch, args.capacity
+    K, W, R = args.steps, args.warmup, args.passes
     # ---- build and prefill the shard (untimed) ---------------------------------
     buf = PrioritizedReplayBuffer(cap, alpha=ALPHA, beta0=BETA0, betasteps=None,
                                   normalize_by_max="memory", num_steps=N_STEP, device=local_rank,
                                   max_batch=max(B, 512), part_capacity=cap + 4096,
-                                  sample_mode=args.mode)
+                                  sample_mode="exact")
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     rng = np.random.RandomState(100 + rank)
@@ -369,11 +406,11 @@ def main():
         buf.append_trajectory(frames, acts, rews, term)
         done += m
     # non-uniform priorities so that the tree descent is not degenerate
-    n_pri = 64
-    for _ in range(n_pri):
+    for _ in range(64):
         np.random.seed(rng.randint(1 << 30))
         buf.sample(B)
         buf.update_errors(torch.rand(B, device=dev, dtype=torch.float32, generator=g) * 2)
+    buf.store.flush()
     torch.cuda.synchronize()
     fill_s = time.perf_counter() - t_fill
     assert len(buf) == cap, (len(buf), cap)
@@ -381,10 +418,6 @@ def main():
     store = buf.store
     phi = ScaleU8()
     gp = buf._gamma_pow(GAMMA)
-    mode = _lib.SAMPLE_EXACT if args.mode == "exact" else _lib.SAMPLE_PARALLEL
-    K, W = args.steps, args.warmup
-    u_all = rng.random_sample((K + W, B))
-    err_dev = torch.rand((16, B), device=dev, dtype=torch.float32, generator=g).abs() * 1.5
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     def barrier():
@@ -392,15 +425,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident loop through the store (C ABI) -----------------
-    ev_pairs = {"sample": [], "gather": [], "update": []}
-
-    # The device-resident loop goes through the C ABI directly with argument
-    # objects built ONCE (static output tensors, cached pointers): four ctypes
-    # calls per step, no allocation, so the host stays far ahead of the ~0.45 ms
-    # device step even on a busy multi-rank box.
-    import ctypes
-
+    # ---- device-resident loops through the C ABI ---------------------------------
+    # Argument objects are built ONCE (static output tensors, cached pointers); a
+    # pass is two ctypes calls: b2rl_per_defer_errors (no launch) and
+    # b2rl_replay_step (the one launch).
     L = _lib.load()
     cvp = ctypes.c_void_p
     stream = cvp(torch.cuda.current_stream().cuda_stream)
@@ -417,80 +445,108 @@ def main():
         state=o_state.data_ptr(), next_state=o_next.data_ptr(), action=o_action.data_ptr(),
         reward=o_reward.data_ptr(), terminal=o_term.data_ptr(), discount=o_disc.data_ptr(),
         step_rewards=None, len=None)
-    batch_out_ref = ctypes.byref(batch_out)
     gp_arr = np.ascontiguousarray(gp, dtype=np.float64)
-    gp_ptr = cvp(gp_arr.ctypes.data)
-    u_base, u_stride = u_all.ctypes.data, u_all.strides[0]
+    n_pass = (K + W) * R
+    # uniforms of all passes, resident in HBM before the timed region (drawn on the host
+    # from the legacy MT stream, like np.random.uniform in collections/prioritized.py:302)
+    u_dev = torch.from_numpy(rng.random_sample((min(n_pass, 4096), B))).to(dev)
+    err_dev = torch.rand((16, B), device=dev, dtype=torch.float32, generator=g).abs() * 1.5
     err_ptrs = [cvp(err_dev[j].data_ptr()) for j in range(16)]
-    h, idx_ptr, w_ptr = store.h, cvp(o_index.data_ptr()), cvp(o_weight.data_ptr())
+    h = store.h
     beta, scale = float(buf.beta), float(phi.b2rl_obs_scale)
 
-    def step_value(i, timed):
-        # per-kernel event pairs on every 4th timed step only
-        timed = timed and (i % 4 == 0)
-        e = [ev() for _ in range(6)] if timed else None
-        if timed:
-            e[0].record()
-        _lib.check(L.b2rl_per_sample(h, cvp(u_base + i * u_stride), B, mode, idx_ptr, None, stream))
-        if timed:
-            e[1].record()
-        _lib.check(L.b2rl_per_weights(h, beta, _lib.NORM_MEMORY, w_ptr, None, stream))
-        if timed:
-            e[2].record()
-        _lib.check(L.b2rl_replay_gather(h, None, B, gp_ptr, _lib.OBS_U8_TO_F32, scale,
-                                        batch_out_ref, stream))
-        if timed:
-            e[3].record()
-            e[4].record()
-        _lib.check(L.b2rl_per_update_errors(h, err_ptrs[i % 16], 0, B, ALPHA, 0.01, 0.0, 1.0,
-                                            stream))
-        if timed:
-            e[5].record()
-            ev_pairs["sample"].append((e[0], e[1]))
-            ev_pairs["gather"].append((e[2], e[3]))
-            ev_pairs["update"].append((e[4], e[5]))
+    def fused_loop(mode):
+        sa = _lib.StepArgs(
+            n=B, mode=mode, u=u_dev.data_ptr(), u_on_device=1, norm=_lib.NORM_MEMORY, beta=beta,
+            gamma_pow_host=gp_arr.ctypes.data, obs_mode=_lib.OBS_U8_TO_F32, obs_scale=scale,
+            index_dev=o_index.data_ptr(), priority_dev=None, weight_dev=o_weight.data_ptr(),
+            prob_dev=None, out=batch_out)
+        sa_ref = ctypes.byref(sa)
+        u_base, u_stride, u_rows = u_dev.data_ptr(), B * 8, u_dev.shape[0]
+        state = {"i": 0}
+
+        def one_pass():
+            i = state["i"]
+            state["i"] = i + 1
+            sa.u = u_base + (i % u_rows) * u_stride
+            _lib.check(L.b2rl_replay_step(h, sa_ref, stream))
+            # the TD errors of this minibatch (inputs of the replay micro-benchmark):
+            # registered now, written back at the head of the next launch
+            _lib.check(L.b2rl_per_defer_errors(h, err_ptrs[i % 16], 0, B, ALPHA, 0.01, 0.0, 1.0))
+
+        for _ in range(W * R):
+            one_pass()
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(K * R):
+            one_pass()
+        t1.record()
+        barrier()
+        _lib.check(L.b2rl_per_flush(h, stream))
+        return t0.elapsed_time(t1)
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()  # samples SM clock / throttle reasons through all timed regions
-    for i in range(W):
-        step_value(i, False)
-    barrier()
-    t0, t1 = ev(), ev()
-    t0.record()
-    for i in range(W, W + K):
-        step_value(i, True)
-    t1.record()
-    barrier()
-    ms_value = t0.elapsed_time(t1)
-    kern_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev_pairs.items()}
-    # diagnostic: how many draws of one more sample found their subtree pre-staged
-    store.sample(u_all[0], mode=mode, want_index=False, want_priority=False)
-    scout_hits = store.info()["scout_hits"]
-    store.update_errors(err_dev[0], ALPHA, 0.01, 0, 1)
+    ms_value = fused_loop(_lib.SAMPLE_EXACT)
+    scout = store.info()["scout_hits"]
+    ms_par = fused_loop(_lib.SAMPLE_PARALLEL)
+
+    # ---- stand-alone kernels (sub-records of the roofline): event pairs around each
+    kern = {"sample_exact": [], "sample_parallel": [], "weights": [], "gather": [], "update": []}
+    batch_out_ref = ctypes.byref(batch_out)
+    u_host = rng.random_sample((24, B))
+    for i in range(24):
+        mode = _lib.SAMPLE_EXACT if i % 2 == 0 else _lib.SAMPLE_PARALLEL
+        e = [ev() for _ in range(8)]
+        e[0].record()
+        _lib.check(L.b2rl_per_sample(h, cvp(u_host[i].ctypes.data), B, mode,
+                                     cvp(o_index.data_ptr()), None, stream))
+        e[1].record()
+        e[2].record()
+        _lib.check(L.b2rl_per_weights(h, beta, _lib.NORM_MEMORY, cvp(o_weight.data_ptr()), None,
+                                      stream))
+        e[3].record()
+        e[4].record()
+        _lib.check(L.b2rl_replay_gather(h, None, B, cvp(gp_arr.ctypes.data), _lib.OBS_U8_TO_F32,
+                                        scale, batch_out_ref, stream))
+        e[5].record()
+        e[6].record()
+        _lib.check(L.b2rl_per_update_errors(h, err_ptrs[i % 16], 0, B, ALPHA, 0.01, 0.0, 1.0,
+                                            stream))
+        e[7].record()
+        if i >= 4:
+            kern["sample_exact" if i % 2 == 0 else "sample_parallel"].append((e[0], e[1]))
+            kern["weights"].append((e[2], e[3]))
+            kern["gather"].append((e[4], e[5]))
+            kern["update"].append((e[6], e[7]))
+    torch.cuda.synchronize()
+    kern_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in kern.items()}
 
     # ---- e2e: public API with host buffers --------------------------------------
     np.random.seed(7 + rank)
     err_host = [[float(x) for x in np.abs(rng.randn(B))] for _ in range(8)]
     pinned = torch.empty((3, B), dtype=torch.float64).pin_memory()
+    R_e2e = max(1, R // 2)
 
-    def step_e2e(i):
-        exps = buf.sample(B)
+    def pass_e2e(i):
+        exps = buf.sample(B)                      # host-drawn uniforms -> H2D, fused launch
         b = batch_experiences(exps, dev, phi, GAMMA)
         pinned[0].copy_(b["weights"], non_blocking=True)
         pinned[1].copy_(b["reward"], non_blocking=True)
         pinned[2].copy_(exps.index, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the D2H read of the step's result
-        buf.update_errors(err_host[i % 8])
+        buf.update_errors(err_host[i % 8])         # host float list -> priorities -> H2D
         return b
 
-    for i in range(W):
-        step_e2e(i)
+    for i in range(W * 4):
+        pass_e2e(i)
     barrier()
     t2, t3 = ev(), ev()
     t2.record()
-    for i in range(K):
-        step_e2e(i)
+    for i in range(K * R_e2e):
+        pass_e2e(i)
     t3.record()
     barrier()
     ms_e2e = t2.elapsed_time(t3)
@@ -503,14 +559,15 @@ def main():
 
         torch.backends.cudnn.allow_tf32 = False  # fp32 parity configuration
         torch.backends.cuda.matmul.allow_tf32 = False
+        graph = (not args.no_rainbow_graph) and world == 1
         agent = make_rainbow_agent(buf, local_rank, B,
                                    grad_sync=parallel.GradSync() if world > 1 else None,
-                                   cuda_graph=args.rainbow_graph and world == 1)
-        vec_steps = max(8, min(K, 40))
+                                   cuda_graph=graph)
+        vec_steps = max(8, min(4 * K, 80))
         res = {}
         for tag, env_dev in (("value", dev), ("e2e", "cpu")):
             env = SyntheticAtariVectorEnv(RAINBOW_ENVS, device=env_dev, seed=11 + rank)
-            rainbow_loop(agent, env, 3)  # warm-up (cuDNN autotune, allocator)
+            rainbow_loop(agent, env, 4)  # warm-up (cuDNN autotune, allocator, graph capture)
             barrier()
             a, b = ev(), ev()
             n0 = agent.optim_t
@@ -519,114 +576,156 @@ def main():
             b.record()
             barrier()
             res[tag] = (a.elapsed_time(b), agent.optim_t - n0)
-        rb = (res, vec_steps)
+        rb = (res, vec_steps, graph)
+
+    # ---- secondary workloads: BASELINE configs[1], [3], [4] -------------------------
+    secondary = None
+    if not args.no_secondary and world == 1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_secondary
+
+            secondary = bench_secondary.run_all(graph=True)
+        except Exception as exc:  # secondary lines never take the headline down
+            secondary = {"error": repr(exc)}
 
     clk = clocks.stop() if rank == 0 else None
 
     # ---- max over ranks ---------------------------------------------------------
-    tm = torch.tensor([ms_value, ms_e2e] + ([rb[0]["value"][0], rb[0]["e2e"][0]] if rb else []),
+    tm = torch.tensor([ms_value, ms_e2e, ms_par] +
+                      ([rb[0]["value"][0], rb[0]["e2e"][0]] if rb else []),
                       device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     tml = [float(x) for x in tm.tolist()]
-    ms_value, ms_e2e = tml[0], tml[1]
+    ms_value, ms_e2e, ms_par = tml[0], tml[1], tml[2]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    total = world * B * K
-    value = total / (ms_value / 1e3)
-    e2e = total / (ms_e2e / 1e3)
+    value = world * B * K * R / (ms_value / 1e3)
+    e2e = world * B * K * R_e2e / (ms_e2e / 1e3)
+    value_par = world * B * K * R / (ms_par / 1e3)
+    ms_pass = ms_value / (K * R)
+    ms_pass_par = ms_par / (K * R)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = json.load(open(peaks_path))["hbm_gbs"]
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
-    gather_bytes = ALGO_BYTES_GATHER * B
-    achieved = gather_bytes / (kern_ms["gather"] * 1e-3) / 1e9
-    traffic = ncu_gather_traffic() if (B == 512 and args.capacity == 10 ** 6) else None
+
+    def roof(bytes_per_launch, ms, kernel, traffic=None, **extra):
+        ach = bytes_per_launch / (ms * 1e-3) / 1e9
+        d = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peak, "unit": "GB/s",
+             "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": bytes_per_launch,
+             "kernel_ms": ms, "peak_source": peak_src}
+        d.update(extra)
+        return d
+
+    full = B == 512 and args.capacity == 10 ** 6
+    sub = {
+        "k_sample_exact_deep": {"ms": kern_ms["sample_exact"],
+                                "ns_per_draw": 1e6 * kern_ms["sample_exact"] / B,
+                                "bound": "latency of the dependent draw chain",
+                                "achieved_GBps": ALGO_BYTES_TREE * B / kern_ms["sample_exact"] / 1e6},
+        "k_sample_parallel": {"ms": kern_ms["sample_parallel"]},
+        "k_weights": {"ms": kern_ms["weights"]},
+        "k_gather": roof(ALGO_BYTES_GATHER * B, kern_ms["gather"], "k_gather",
+                         traffic=ncu_traffic("gather") if full else None),
+        "k_update_paths": {"ms": kern_ms["update"]},
+    }
     line = {
         "metric": "replay_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_value / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 priorities / u8->f32 frames",
-        "data": "synthetic", "config": workload_config(args, world),
-        "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": 8 * B + 8 * B + 8 * (N_STEP + 1),
-                "d2h_bytes_per_step": 4 * B + 4 * B + 8 * B},
-        "gpu_launches": 4 * K,
-        "kernels_ms": kern_ms,
-        "roofline": {"bound": "hbm", "kernel": "k_gather", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "profiles/*_ncu_full_summary.csv (ncu --set full, per launch)",
-                     "algorithmic_bytes_per_launch": gather_bytes, "peak_source": peak_src,
-                     "kernel_ms": kern_ms["gather"],
-                     "share_of_step": kern_ms["gather"] / (ms_value / K)},
-        "sampler": {"mode": args.mode, "kernel": "k_sample_" + args.mode,
-                    "ms_per_batch": kern_ms["sample"],
-                    "ns_per_draw": 1e6 * kern_ms["sample"] / B, "scout_prefetch_hits": scout_hits & 0xffff, "scout_not_ready": scout_hits >> 16,
-                    "share_of_step": kern_ms["sample"] / (ms_value / K)},
+        "data": "synthetic", "config": workload_config(args, world, passes=R),
+        "e2e": {"value": e2e, "unit": "samples/s", "ms_per_pass": ms_e2e / (K * R_e2e),
+                "passes_per_step": R_e2e,
+                "h2d_bytes_per_step": R_e2e * (8 * B + 8 * B),
+                "d2h_bytes_per_step": R_e2e * (4 * B + 4 * B + 8 * B)},
+        "gpu_launches": K * R,
+        "ms_per_pass": ms_pass,
+        # the PATH: SURVEY 8(d) bytes per sample x samples per launch / launch time
+        "roofline": roof(ALGO_BYTES_PATH * B, ms_pass, "k_replay_step<exact> (whole pass: "
+                         "write-back + sample + weights + gather in one launch)",
+                         traffic=ncu_traffic("step_exact") if full else None,
+                         dominant_phase="exact sampler (dependent chain of %d draws)" % B,
+                         traffic_source="profiles/r*_ncu_full_summary.csv (ncu --set full, per launch)",
+                         algorithmic_bytes_per_sample=ALGO_BYTES_PATH, kernels=sub),
+        "sampler": {"mode": "exact", "ns_per_draw_fused_pass": 1e6 * ms_pass / B,
+                    "ns_per_draw_kernel": 1e6 * kern_ms["sample_exact"] / B,
+                    "scout_prefetch_hits": scout & 0xffff, "scout_not_ready": scout >> 16},
+        "throughput_mode": {
+            "sampler": "parallel (all descents concurrent on the frozen tree, with replacement; "
+                       "not index-identical to the reference)",
+            "value": value_par, "unit": "samples/s", "ms_per_pass": ms_pass_par,
+            "gpu_launches": K * R,
+            "roofline": roof(ALGO_BYTES_PATH * B, ms_pass_par, "k_replay_step<parallel>",
+                             traffic=ncu_traffic("step_parallel") if full else None)},
+        "separate_launches_ms": kern_ms,
         "clocks": clk, "prefill_s": fill_s,
         "hbm_bytes_per_rank": store.device_bytes,
     }
     if rb is not None:
-        res, vec_steps = rb
+        res, vec_steps, graph = rb
         steps_total = world * RAINBOW_ENVS * vec_steps
         line["rainbow"] = {
-            "env_steps_per_sec": steps_total / (tml[2] / 1e3),
-            "e2e_env_steps_per_sec": steps_total / (tml[3] / 1e3),
+            "env_steps_per_sec": steps_total / (tml[3] / 1e3),
+            "e2e_env_steps_per_sec": steps_total / (tml[4] / 1e3),
             "num_envs_per_rank": RAINBOW_ENVS, "vector_steps": vec_steps,
             "updates": res["value"][1], "update_interval": RAINBOW_UPDATE_INTERVAL,
-            "ms_per_update_incl_acting": tml[2] / max(res["value"][1], 1),
-            "minibatch_per_rank": B, "dtype": "fp32 (TF32 off)",
+            "ms_per_update_incl_acting": tml[3] / max(res["value"][1], 1),
+            "minibatch_per_rank": B, "dtype": "fp32 (TF32 off)", "cuda_graph": graph,
             "model": "DistributionalDuelingDQN(18, 51) + factorized noisy, Adam(6.25e-5)",
             "note": "value: GPU-resident synthetic env; e2e: host numpy env (frames H2D, "
                     "actions D2H); gradient all-reduce (NCCL) when n_gpus > 1"}
+    if secondary is not None:
+        line["secondary"] = secondary
     if not args.no_cpu_baseline:
-        if rb is not None:
-            rc = cpu_rainbow_run(cap, B, 10.0)
+        r, rc = cpu_arm(cap, B, 10 ** 9, 2, args.cpu_seconds, 10.0 if rb is not None else None)
+        if rc is not None:
             line["rainbow"]["cpu_baseline"] = {
-                "value": rc["env_steps_per_sec"], "unit": "env-steps/s", "kind": "port",
+                "value": rc["env_steps_per_sec"], "unit": "env-steps/s", "kind": rc["kind"],
                 "cores": rc["threads"], "ms_per_update": rc["ms_per_update"],
-                "sample": "%.0f s of the same loop on the host (oracle/pyport_rainbow.py)"
-                          % rc["seconds"]}
-        r = cpu_reference_run(cap, B, 10 ** 9, 2, seconds=args.cpu_seconds)
+                "sample": "%.0f s of the same loop on the host" % rc["seconds"]}
         line["cpu_baseline"] = {
-            "value": r["samples_per_sec"], "unit": "samples/s", "cores": 1, "kind": "port",
-            "host_cores_available": os.cpu_count(),
-            "sample": "%d steps (%.1f s) of sample(%d)+batch_experiences+update_errors, "
-                      "1M-leaf tree, frames from a pool of %d; pure-Python port of the "
-                      "reference (oracle/pyport.py)" % (r["steps"], r["seconds"], B, r["pool"])}
+            "value": r["samples_per_sec"], "unit": "samples/s", "cores": r["cores"],
+            "kind": r["kind"], "host_cores_available": os.cpu_count(),
+            "sample": cpu_sample_text(r, B)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def ncu_gather_traffic():
-    """dram__bytes_read + dram__bytes_write of k_gather per launch, from the
+def ncu_traffic(kernel):
+    """dram__bytes_read + dram__bytes_write of `kernel` per launch, from the
     newest committed ncu --set full summary under profiles/ (bytes)."""
     import csv
     import glob
 
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")))
-    if not files:
-        return None
     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    total = 0.0
-    for row in csv.reader(open(files[-1])):
-        if len(row) == 4 and row[0] == "gather" and row[1] in ("dram__bytes_read.sum",
-                                                             "dram__bytes_write.sum"):
-            total += float(row[2]) * mult.get(row[3], 1)
-    return total or None
+    for f in reversed(files):
+        total = 0.0
+        for row in csv.reader(open(f)):
+            if len(row) == 4 and row[0] == kernel and row[1] in ("dram__bytes_read.sum",
+                                                               "dram__bytes_write.sum"):
+                total += float(row[2]) * mult.get(row[3], 1)
+        if total:
+            return total
+    return None
 
 
-def workload_config(args, world):
+def workload_config(args, world, passes):
     return {"workload": "Rainbow replay path (BASELINE configs[2]): PER 1M cap, 3-step, "
                         "84x84x4 u8 frames, minibatch %d per rank" % args.batch,
             "capacity_per_rank": args.capacity, "batch_per_rank": args.batch,
             "global_batch": args.batch * world, "n_step": N_STEP, "alpha": ALPHA,
-            "sampler": args.mode, "obs_out": "f32 (x/255)", "l2": "inputs_larger_than_l2",
+            "passes_per_step": passes,
+            "pass": "priority write-back of the previous minibatch + sample + IS weights + gather",
+            "sampler": "exact", "obs_out": "f32 (x/255)", "l2": "inputs_larger_than_l2",
             "parallelism": "replay shard per rank, no data-path collective"}
 
 

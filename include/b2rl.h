@@ -225,6 +225,52 @@ int b2rl_replay_gather(b2rl_replay *h, const int64_t *index_dev, int32_t n,
                        void *stream);
 
 /* ------------------------------------------------------------------------
+ * Fused replay step: ONE persistent launch per minibatch that
+ *   1. writes back the priorities of the PREVIOUS sample if its TD errors were
+ *      registered with b2rl_per_defer_errors (set_last_priority,
+ *      collections/prioritized.py:107-116),
+ *   2. draws n leaves (b2rl_per_sample semantics) and computes their
+ *      importance weights (b2rl_per_weights semantics),
+ *   3. gathers the minibatch (b2rl_replay_gather semantics); the gather CTAs
+ *      consume the draws 32 at a time while the sampler is still drawing.
+ * Replaces the reference's update loop body around
+ * pfrl/replay_buffer.py:329-356 -> pfrl/replay_buffers/prioritized.py:117-126
+ * -> pfrl/replay_buffer.py:157-212.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+    int32_t n;             /* draws                                          */
+    int32_t mode;          /* b2rl_sample_mode                               */
+    const double *u;       /* n uniforms in [0,1), reference order           */
+    int32_t u_on_device;   /* 0: host memory (copied through a pinned ring),
+                              1: device memory, alive until the stream has
+                              passed the call                                */
+    int32_t norm;          /* b2rl_weight_norm                               */
+    double beta;           /* IS exponent                                    */
+    const double *gamma_pow_host; /* gamma**i, i = 0..n_step (host)          */
+    int32_t obs_mode;      /* b2rl_obs_mode                                  */
+    float obs_scale;
+    int64_t *index_dev;    /* [n] logical indices, or NULL                   */
+    double *priority_dev;  /* [n] priorities found, or NULL                  */
+    float *weight_dev;     /* [n] importance weights, or NULL                */
+    double *prob_dev;      /* [n] probabilities, or NULL                     */
+    b2rl_batch_out out;    /* any pointer may be NULL                        */
+} b2rl_step_args;
+
+int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *args, void *stream);
+
+/* Answer the last sample with TD errors on the device WITHOUT launching: the
+ * write-back runs at the head of the next b2rl_replay_step launch, or before
+ * the next call that reads or writes the trees (append, sample, get_info, ...),
+ * whichever comes first -- so every later operation sees exactly the state
+ * b2rl_per_update_errors would have left.  err_dev must stay alive and
+ * unchanged until then.  Same arguments as b2rl_per_update_errors. */
+int b2rl_per_defer_errors(b2rl_replay *h, const void *err_dev, int err_is_f64,
+                          int32_t n, double alpha, double eps,
+                          double error_min, double error_max);
+/* Apply a deferred write-back now (no-op if none is registered). */
+int b2rl_per_flush(b2rl_replay *h, void *stream);
+
+/* ------------------------------------------------------------------------
  * Fused loss kernels (fp32, device pointers, deterministic reductions).
  * `mean` != 0: divide the batch sum by B ("mean" batch_accumulator).
  * `weights` may be NULL (uniform replay).  `scratch` is B floats.

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libb2rl.so")
-SOURCES = ["replay.cu", "sampler.cu", "gather.cu", "losses.cu", "ppo.cu", "conv.cu"]
+SOURCES = ["replay.cu", "sampler.cu", "step.cu", "gather.cu", "losses.cu", "ppo.cu", "conv.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -37,7 +37,8 @@ def _sources():
 def build(force=False, verbose=False):
     """Compile libb2rl.so in-tree with nvcc for sm_100a (no GPU needed)."""
     srcs = _sources()
-    deps = srcs + [os.path.join(CSRC, "b2rl_internal.cuh"), os.path.join(INCLUDE, "b2rl.h")]
+    deps = srcs + [os.path.join(CSRC, "b2rl_internal.cuh"), os.path.join(CSRC, "tree_dev.cuh"),
+                   os.path.join(INCLUDE, "b2rl.h")]
     if (
         not force
         and os.path.exists(LIB_PATH)
@@ -93,6 +94,25 @@ class BatchOut(ctypes.Structure):
     ]
 
 
+class StepArgs(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int32),
+        ("mode", ctypes.c_int32),
+        ("u", ctypes.c_void_p),
+        ("u_on_device", ctypes.c_int32),
+        ("norm", ctypes.c_int32),
+        ("beta", ctypes.c_double),
+        ("gamma_pow_host", ctypes.c_void_p),
+        ("obs_mode", ctypes.c_int32),
+        ("obs_scale", ctypes.c_float),
+        ("index_dev", ctypes.c_void_p),
+        ("priority_dev", ctypes.c_void_p),
+        ("weight_dev", ctypes.c_void_p),
+        ("prob_dev", ctypes.c_void_p),
+        ("out", BatchOut),
+    ]
+
+
 class PerInfo(ctypes.Structure):
     _fields_ = [
         ("total", ctypes.c_double),
@@ -132,6 +152,9 @@ SIGNATURES = {
     "b2rl_per_get_info": (_int, [_vp, ctypes.POINTER(PerInfo), _vp]),
     "b2rl_per_read_priorities": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "b2rl_per_set_max_priority": (_int, [_vp, _dbl, _vp]),
+    "b2rl_replay_step": (_int, [_vp, ctypes.POINTER(StepArgs), _vp]),
+    "b2rl_per_defer_errors": (_int, [_vp, _vp, _int, _i32, _dbl, _dbl, _dbl, _dbl]),
+    "b2rl_per_flush": (_int, [_vp, _vp]),
     "b2rl_replay_gather": (
         _int, [_vp, _vp, _i32, _vp, _int, ctypes.c_float, ctypes.POINTER(BatchOut), _vp]),
     "b2rl_c51_loss_fwd": (_int, [_vp] * 7 + [_i32, _i32, _int] + [_vp] * 5),

@@ -42,6 +42,8 @@ struct B2rlDevState {
     int pad;
 };
 
+static constexpr int B2RL_U_RING = 8;
+
 // ---- the handle --------------------------------------------------------------
 struct b2rl_replay {
     b2rl_replay_config cfg;
@@ -75,6 +77,19 @@ struct b2rl_replay {
     int last_n;
     int last_mode;
 
+    // fused replay step (step.cu): cross-CTA "draws ready" counter, launch sequence
+    // number, ring of pinned slots for host-drawn uniforms, deferred write-back
+    unsigned long long *ready_dev;
+    uint64_t step_seq;
+    double *u_ring_pin, *u_ring_dev;
+    cudaEvent_t u_ev[B2RL_U_RING];
+    uint64_t u_head;
+    int sm_count;
+    bool pending;          // TD errors of the last sample registered, trees not yet updated
+    const void *pend_err;
+    int pend_is_f64, pend_n;
+    double pend_alpha, pend_eps, pend_emin, pend_emax;
+
     // staging (host pinned + device), guarded by an event
     uint8_t *pin;
     uint8_t *stage;
@@ -93,6 +108,15 @@ static inline int b2rl_ilog2(int64_t x)
 // Make sure the staging buffers hold `bytes`; waits for the previous user.
 int b2rl_stage_acquire(b2rl_replay *h, size_t bytes);
 int b2rl_stage_release(b2rl_replay *h, cudaStream_t s);
+
+// "Last CTA finishes the reduction" elections use one of B2RL_N_TICKETS device
+// counters per LAUNCH (rotating ticket, self-resetting atomicInc), so launches
+// that overlap on different streams never share a counter.
+static constexpr unsigned B2RL_N_TICKETS = 256;
+unsigned b2rl_next_ticket();
+
+// Apply a write-back registered with b2rl_per_defer_errors (no-op if none).
+int b2rl_flush_pending(b2rl_replay *h, cudaStream_t s);
 
 // Kernel launchers implemented in the other TUs.
 // Recompute the ancestors of up to 4 contiguous leaf-node ranges [lo, hi]

@@ -141,11 +141,13 @@ extern "C" int b2rl_conv_nature1_fwd(const float *x, const float *w, const float
     B2RL_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 7) == 0, B2RL_ERR_INVALID,
                  "conv_nature1_fwd: x must be 16-byte aligned, out 8-byte aligned");
     const size_t smem = sizeof(float) * (IMG + WSZ) + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64]; // per device
+    int cur_dev = 0;
+    B2RL_CUDA(cudaGetDevice(&cur_dev));
+    if (cur_dev < 0 || cur_dev >= 64 || !attr_set[cur_dev]) {
         B2RL_CUDA(cudaFuncSetAttribute(k_conv_nature1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-        attr_set = true;
+        if (cur_dev >= 0 && cur_dev < 64) attr_set[cur_dev] = true;
     }
     static int sm_count = 0;
     if (!sm_count) {

@@ -17,7 +17,7 @@
 
 namespace {
 
-__device__ unsigned int g_done_counter = 0;
+__device__ unsigned int g_done_counter[B2RL_N_TICKETS]; // zero-initialised, self-resetting
 
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -27,13 +27,14 @@ __device__ __forceinline__ float warp_sum(float v)
 
 // Deterministic final reduction: the last CTA to arrive sums term[i] for
 // i < n in a fixed order and writes *out = sum / divisor.
-__device__ void finish_sum(const float *term, int n, float divisor, float *out, float *sh)
+__device__ void finish_sum(const float *term, int n, float divisor, float *out, float *sh,
+                           unsigned ticket)
 {
     __shared__ bool last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int prev = atomicInc(&g_done_counter, gridDim.x - 1);
+        const unsigned int prev = atomicInc(&g_done_counter[ticket], gridDim.x - 1);
         last = (prev == gridDim.x - 1);
     }
     __syncthreads();
@@ -68,6 +69,7 @@ struct C51Args {
     float *delta_out; // [B] per-sample loss = priority error
     float *term;      // [B] scratch: w_i * delta_i
     float *loss_out;  // [1]
+    unsigned ticket;  // completion counter of this launch
 };
 
 __global__ void __launch_bounds__(C51_WARPS * 32) k_c51_fwd(C51Args a)
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(C51_WARPS * 32) k_c51_fwd(C51Args a)
             a.term[i] = a.weights ? __fmul_rn(acc, a.weights[i]) : acc;
         }
     }
-    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh);
+    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh, a.ticket);
 }
 
 struct C51BwdArgs {
@@ -143,6 +145,7 @@ struct TdArgs {
     const float *reward, *discount, *terminal, *weights;
     int B, nA, clip_delta, mean;
     float *y_out, *t_out, *delta_out, *term, *loss_out;
+    unsigned ticket;
 };
 
 __global__ void __launch_bounds__(256) k_td_fwd(TdArgs a)
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256) k_td_fwd(TdArgs a)
         a.delta_out[i] = ad;
         a.term[i] = a.weights ? __fmul_rn(l, a.weights[i]) : l;
     }
-    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh);
+    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh, a.ticket);
 }
 
 struct TdBwdArgs {
@@ -201,6 +204,7 @@ struct QhArgs {
     const float *y, *t, *taus, *weights;
     int B, N, Np, mean;
     float *delta_out, *term, *loss_out;
+    unsigned ticket;
 };
 
 // one CTA per sample, N x N' pairs strided over the threads
@@ -238,7 +242,7 @@ __global__ void __launch_bounds__(256) k_qh_fwd(QhArgs a)
         a.delta_out[i] = s_tot / (float)(a.N * a.Np); // eltwise_loss.mean((1, 2)), iqn.py:388
         a.term[i] = a.weights ? __fmul_rn(li, a.weights[i]) : li;
     }
-    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh);
+    finish_sum(a.term, a.B, a.mean ? (float)a.B : 1.0f, a.loss_out, sh, a.ticket);
 }
 
 struct QhBwdArgs {
@@ -280,6 +284,7 @@ extern "C" int b2rl_c51_loss_fwd(const float *y, const float *next_p, const floa
                  "c51_loss_fwd: need B > 0 and 2 <= n_atoms <= %d", C51_MAX_ATOMS);
     C51Args a{y, next_p, reward, discount, terminal, weights, z, B, n_atoms, mean,
               t_out, delta_out, scratch, loss_out};
+    a.ticket = b2rl_next_ticket();
     k_c51_fwd<<<(B + C51_WARPS - 1) / C51_WARPS, C51_WARPS * 32, 0, (cudaStream_t)stream>>>(a);
     B2RL_CUDA(cudaGetLastError());
     return B2RL_OK;
@@ -310,6 +315,7 @@ extern "C" int b2rl_td_loss_fwd(const float *q, const int64_t *action, const flo
     B2RL_REQUIRE(B > 0 && n_actions > 0, B2RL_ERR_RANGE, "td_loss_fwd: empty batch");
     TdArgs a{q, (const long long *)action, next_q, reward, discount, terminal, weights, B,
              n_actions, clip_delta, mean, y_out, t_out, delta_out, scratch, loss_out};
+    a.ticket = b2rl_next_ticket();
     k_td_fwd<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
     B2RL_CUDA(cudaGetLastError());
     return B2RL_OK;
@@ -339,6 +345,7 @@ extern "C" int b2rl_quantile_huber_fwd(const float *y, const float *t, const flo
                  "quantile_huber_fwd: null argument");
     B2RL_REQUIRE(B > 0 && N > 0 && Np > 0, B2RL_ERR_RANGE, "quantile_huber_fwd: empty");
     QhArgs a{y, t, taus, weights, B, N, Np, mean, delta_out, scratch, loss_out};
+    a.ticket = b2rl_next_ticket();
     k_qh_fwd<<<B, 256, 0, (cudaStream_t)stream>>>(a);
     B2RL_CUDA(cudaGetLastError());
     return B2RL_OK;

@@ -20,7 +20,7 @@
 
 namespace {
 
-__device__ unsigned int g_gae_counter = 0;
+__device__ unsigned int g_gae_counter[B2RL_N_TICKETS]; // zero-initialised, self-resetting
 
 struct GaeArgs {
     const float *reward, *nonterminal, *v, *v_next; // [T, E]
@@ -31,6 +31,7 @@ struct GaeArgs {
     float *adv, *v_teacher; // [T, E]
     double *partial;        // [gridDim.x, 3] (count, sum, sumsq) scratch
     float *stats;           // [2] mean, std (unbiased=False) over valid entries
+    unsigned ticket;        // completion counter of this launch
 };
 
 __global__ void __launch_bounds__(128) k_gae(GaeArgs a)
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) k_gae(GaeArgs a)
         a.partial[blockIdx.x * 3 + 1] = x;
         a.partial[blockIdx.x * 3 + 2] = y;
         __threadfence();
-        const unsigned int prev = atomicInc(&g_gae_counter, gridDim.x - 1);
+        const unsigned int prev = atomicInc(&g_gae_counter[a.ticket], gridDim.x - 1);
         last = (prev == gridDim.x - 1);
     }
     __syncthreads();
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(128) k_gae(GaeArgs a)
 // ---------------------------------------------------------------------------
 // PPO loss: forward value + the three gradients in one pass.
 // ---------------------------------------------------------------------------
-__device__ unsigned int g_ppo_counter = 0;
+__device__ unsigned int g_ppo_counter[B2RL_N_TICKETS];
 
 struct PpoArgs {
     const float *log_prob, *entropy, *v_pred;              // [M] (require grad)
@@ -120,6 +121,7 @@ struct PpoArgs {
     float *g_log_prob, *g_entropy, *g_v_pred; // [M] d loss / d input
     double *partial;  // [gridDim.x, 3]
     float *losses;    // [4] total, policy, value, entropy
+    unsigned ticket;
 };
 
 __global__ void __launch_bounds__(256) k_ppo_loss(PpoArgs a)
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(256) k_ppo_loss(PpoArgs a)
         a.partial[blockIdx.x * 3 + 1] = y;
         a.partial[blockIdx.x * 3 + 2] = z;
         __threadfence();
-        const unsigned int prev = atomicInc(&g_ppo_counter, gridDim.x - 1);
+        const unsigned int prev = atomicInc(&g_ppo_counter[a.ticket], gridDim.x - 1);
         last = (prev == gridDim.x - 1);
     }
     __syncthreads();
@@ -222,6 +224,7 @@ extern "C" int b2rl_gae(const float *reward, const float *nonterminal, const flo
     B2RL_REQUIRE(T > 0 && E > 0, B2RL_ERR_RANGE, "gae: empty rollout");
     GaeArgs a{reward, nonterminal, v, v_next, cut, valid, T, E, gamma, lambda,
               adv, v_teacher, scratch, stats};
+    a.ticket = b2rl_next_ticket();
     k_gae<<<(E + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     B2RL_CUDA(cudaGetLastError());
     return B2RL_OK;
@@ -243,6 +246,7 @@ extern "C" int b2rl_ppo_loss(const float *log_prob, const float *entropy, const 
     PpoArgs a{log_prob, entropy, v_pred, log_prob_old, v_pred_old, adv, v_teacher, adv_stats, M,
               clip_eps, clip_eps_vf, value_coef, entropy_coef, g_log_prob, g_entropy, g_v_pred,
               scratch, losses};
+    a.ticket = b2rl_next_ticket();
     k_ppo_loss<<<(M + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
     B2RL_CUDA(cudaGetLastError());
     return B2RL_OK;

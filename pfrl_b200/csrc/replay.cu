@@ -17,6 +17,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 
 #include "b2rl_internal.cuh"
@@ -30,6 +31,12 @@ void b2rl_set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+unsigned b2rl_next_ticket()
+{
+    static std::atomic<unsigned> t{0};
+    return t.fetch_add(1, std::memory_order_relaxed) % B2RL_N_TICKETS;
 }
 
 extern "C" const char *b2rl_last_error(void) { return g_err; }
@@ -326,6 +333,11 @@ extern "C" int b2rl_replay_destroy(b2rl_replay *h)
         if (p) cudaFree(p);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
+    if (h->ready_dev) cudaFree(h->ready_dev);
+    if (h->u_ring_dev) cudaFree(h->u_ring_dev);
+    if (h->u_ring_pin) cudaFreeHost(h->u_ring_pin);
+    for (int i = 0; i < B2RL_U_RING; i++)
+        if (h->u_ev[i]) cudaEventDestroy(h->u_ev[i]);
     delete h;
     return B2RL_OK;
 }
@@ -438,6 +450,9 @@ extern "C" int b2rl_replay_append(b2rl_replay *h, const b2rl_experiences *e, int
     cudaStream_t s = (cudaStream_t)stream;
     B2RL_CUDA(cudaSetDevice(h->cfg.device));
     const b2rl_replay_config &c = h->cfg;
+    // a deferred write-back precedes the append: the new leaves take the
+    // max_priority it may raise (collections/prioritized.py:42-44,114)
+    TRY(b2rl_flush_pending(h, s));
 
     AppendArgs a;
     a.state_parts = h->state_parts;

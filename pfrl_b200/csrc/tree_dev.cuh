@@ -1,0 +1,881 @@
+// tree_dev.cuh -- device-side building blocks on the dense fp64 heaps, shared
+// by the stand-alone kernels (sampler.cu) and the fused replay step (step.cu):
+//
+//   exact_deep<D, FMA>()   bit-exact sequential sampler (main warp + two scout
+//                          warps + a publisher warp)
+//   sample_parallel()      all descents concurrently on the frozen tree
+//   tree_update_paths()    priority write-back for <= 512 leaves: sorted
+//                          paths, siblings prefetched in ONE round trip, the
+//                          level loop runs on shared memory only
+//
+// Reference semantics (pure Python, pfrl/collections/prioritized.py):
+//   :245-258 _find, :294-312 prioritized_sample, :107-116 set_last_priority,
+//   :140-180 _reduce / _write; pfrl/replay_buffers/prioritized.py:47-66
+//   priority_from_errors / weights_from_probabilities.
+#pragma once
+#include <math.h>
+
+#include "b2rl_internal.cuh"
+
+static constexpr int TOP_LEVELS = 14; // heap levels 0..13 -> 16383 nodes = 128 KB
+
+struct SampleArgs {
+    double *sum;
+    const double *mn;
+    B2rlDevState *st;
+    const double *u;
+    int n;
+    int levels;      // leaves are at heap level `levels`
+    long long nslots;
+    int T;           // levels held in shared memory (nodes [1, 2^T))
+    int D;           // levels below the shared part (0: leaves are in shared)
+    int32_t *slots_out;
+    double *prio_out;
+    long long *index_out; // optional
+    double *prio_user;    // optional
+    // importance weights computed by the sampler itself (fused step); weight
+    // and prob may be null (replay_buffers/prioritized.py:57-66)
+    float *weight;
+    double *prob;
+    double beta;
+    int norm;
+    // publication of completed draws to other CTAs (fused step), or null:
+    // *ready = seq_base | (number of draws whose outputs are visible)
+    unsigned long long *ready;
+    unsigned long long seq_base;
+};
+
+// ---------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------
+// L2 residency: the sum tree (32 MB at 1M capacity) is re-read by every draw
+// while the gather streams ~140 MB per minibatch through the same L2.  Tree
+// accesses carry an evict_last policy (the gather's stores are .cs).
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ double2 ld_tree_pair(const double2 *ptr, uint64_t pol)
+{
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(ptr), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ void st_tree(double *ptr, double v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    while (!mbar_try_wait(bar, phase)) {
+    }
+}
+
+// cp.async.bulk (SASS UBLKCP): global -> shared, completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_smem(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_smem(int *p, int v)
+{
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// importance-sampling weight of one draw (replay_buffers/prioritized.py:57-66,
+// probabilities of collections/prioritized.py:79-82 with uniform_ratio == 0)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float is_weight(double prob, double denom, double len, double beta,
+                                           int norm)
+{
+    const double base = (norm == B2RL_NORM_NONE) ? len * prob : prob / denom;
+    return (float)pow(base, -beta);
+}
+
+// ---------------------------------------------------------------------------
+// speculative lane-parallel descent (see sampler.cu header comment)
+//
+// The conditional subtraction `if (right) x -= left` is ONE fused multiply-add
+// with a lane-constant multiplier: fma(-1, left, x) rounds x - left once,
+// exactly like __dsub_rn; fma(-0, left, x) = x + (-0) = x because tree values
+// are finite and >= 0.  The arithmetic of the winning lane is therefore bit
+// for bit the reference's (validated on a B200: bit-identity suite green,
+// 741 vs 802 ns/draw).  FMA = false keeps the subtract + select form.
+// ---------------------------------------------------------------------------
+template <int R, bool FMA>
+__device__ __forceinline__ void spec_round(const double *val, int &node, double &pos, int lane)
+{
+    static_assert(R >= 1 && R <= 5, "one round covers at most 5 levels");
+    const int li = lane & ((1 << R) - 1);
+    double left[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int nj = (node << j) + (li >> (R - j));
+        left[j] = val[2 * nj];
+    }
+    double x = pos;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const bool right = (li >> (R - 1 - j)) & 1;
+        const bool lt = x < left[j];
+        ok = ok && (lt != right);
+        if constexpr (FMA) {
+            x = __fma_rn(right ? -1.0 : -0.0, left[j], x);
+        } else {
+            if (right) x = __dsub_rn(x, left[j]);
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if constexpr (R < 5) m &= (1u << (1 << R)) - 1u;
+    const int win = __ffs(m) - 1;
+    pos = __shfl_sync(0xffffffffu, x, win);
+    node = (node << R) + win;
+}
+
+template <int L, bool FMA = true>
+__device__ __forceinline__ void spec_descend(const double *val, int &node, double &pos, int lane)
+{
+    if constexpr (L > 0) {
+        constexpr int R = L >= 5 ? 5 : L;
+        spec_round<R, FMA>(val, node, pos, lane);
+        spec_descend<L - R, FMA>(val, node, pos, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// EXACT sampler for deep trees (levels >= TOP_LEVELS).  Called by ALL threads
+// of the CTA (it uses __syncthreads); warps >= 4 only take part in the
+// barriers.
+//   warp 0 (main)      walks the draws in order, exactly as the reference does
+//   warps 1, 2 (scouts) run a couple of draws ahead on the not-yet-final tree,
+//                      predict which level-13 node a future draw will pick and
+//                      stage that node's lower levels in shared memory, so the
+//                      main warp's only global round trip per draw is usually
+//                      done when it gets there (measured: ~99 % of the draws)
+//   warp 3 (publisher) moves finished draws to global memory 32 at a time,
+//                      computes their importance weights and (fused step)
+//                      releases them to the gather CTAs
+// The prediction is only a prefetch hint: the main warp uses the staged copy
+// iff the predicted node equals the node its own exact descent reached AND no
+// draw in flight when the copy was taken could have changed that subtree
+// (release/acquire on `main_done` + "node != previous node").  The arithmetic
+// of the main warp is the reference's, so indices stay bit-identical.
+// Shared memory: [top 2^14 f64][sub_own 2^(D+1)][sub_pref 3 x 2^(D+1)]
+// [o_prio ring][2 f64][o_slot ring][flags][mbarrier].
+// ---------------------------------------------------------------------------
+static constexpr int EX_RING = 64;    // finished draws waiting for the publisher
+static constexpr int EX_NSCOUT = 2;
+static constexpr int EX_LAG = 2;
+static constexpr int EX_NBUF = EX_LAG + 1;
+
+template <int D>
+__host__ __device__ constexpr size_t exact_deep_smem_bytes()
+{
+    return sizeof(double) * ((size_t(1) << TOP_LEVELS) + (size_t(2) << D) * (1 + EX_NBUF) +
+                             EX_RING + 2) +
+           sizeof(int) * (EX_RING + 16) + 16;
+}
+
+template <int D, bool FMA>
+__device__ __forceinline__ void exact_deep(const SampleArgs &a, double *smem_d)
+{
+    constexpr int T = TOP_LEVELS;
+    constexpr int TOPN = 1 << T;
+    constexpr int SUBN = 2 << D;
+    constexpr int PAIRS = (1 << D) - 1; // child pairs below the chosen top node
+    constexpr int NIT = (PAIRS + 31) / 32;
+    constexpr int CHUNK = 32;
+    constexpr int NSCOUT = EX_NSCOUT, LAG = EX_LAG, NBUF = EX_NBUF, RING = EX_RING;
+    constexpr int F_READY = 0, F_NODE = 4, F_DONE = 8, F_PUB = 9;
+    double *top = smem_d;
+    double *sub_own = smem_d + TOPN;
+    double *sub_pref = sub_own + SUBN;              // [NBUF][SUBN]
+    double *o_prio = sub_pref + NBUF * SUBN;        // [RING]
+    double *s_stat = o_prio + RING;                 // total, min-root
+    int *o_slot = reinterpret_cast<int *>(s_stat + 2); // [RING]
+    int *flags = o_slot + RING; // ready_seq[NBUF] @0, pred_node[NBUF] @4, main_done @8, pub_done @9
+    uint64_t *bar = reinterpret_cast<uint64_t *>(flags + 16);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; i++) flags[i] = -1;
+        flags[F_DONE] = 0;
+        flags[F_PUB] = 0;
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        // earlier generic-proxy writes to the tree by this CTA (fused write-back)
+        // must be visible to the bulk copy engine
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(bar, TOPN * 8);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            bulk_g2s(top + c * (TOPN / 4), a.sum + c * (TOPN / 4), TOPN * 2, bar);
+    }
+    __syncthreads();
+    if (warp < 4) mbar_wait(bar, 0);
+
+    const long long mask = a.nslots - 1;
+    const long long npop = a.st->npop;
+    const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+    const uint64_t pol = policy_evict_last();
+    const double2 *sum2 = reinterpret_cast<const double2 *>(a.sum);
+
+    if (warp >= 1 && warp <= NSCOUT) {
+        // ------------------------------ scouts -------------------------------
+        for (int k = warp; k < a.n; k += NSCOUT) {
+            const double uk = a.u[k];
+            // draws 0..k-1-LAG must be complete (their stores visible) before we read
+            while (ld_acquire_smem(&flags[F_DONE]) < k - LAG) __nanosleep(64);
+            double pos = uk * top[1]; // approximate: up to LAG draws still in flight
+            int node = older;
+            {
+                const double left = top[older];
+                if (!(pos < left)) { pos -= left; node = older ^ 1; }
+            }
+            spec_descend<T - 2, FMA>(top, node, pos, lane);
+            double *dst = sub_pref + (k % NBUF) * SUBN;
+            const unsigned unode = (unsigned)node;
+            double2 tmp[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                int q = lane + 32 * it;
+                q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                const int dq = 31 - __clz(q);
+                tmp[it] = ld_tree_pair(sum2 + ((unode << dq) + (unsigned)(q - (1 << dq))), pol);
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                int q = lane + 32 * it;
+                q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                reinterpret_cast<double2 *>(dst)[q] = tmp[it];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                flags[F_NODE + (k % NBUF)] = node;
+                st_release_smem(&flags[F_READY + (k % NBUF)], k);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 0) {
+        // ------------------------------- main --------------------------------
+        if (lane == 0) {
+            const double total = top[1]; // priority_sums.sum(), :58
+            const double mroot = a.mn[1]; // priority_mins.min(), :59
+            a.st->last_total = total;
+            a.st->last_min = mroot;
+            a.st->last_n = a.n;
+            s_stat[0] = total;
+            s_stat[1] = mroot;
+        }
+        int prev_node[LAG];
+#pragma unroll
+        for (int i = 0; i < LAG; i++) prev_node[i] = -1;
+        int hits = 0, late = 0;
+        for (int k0 = 0; k0 < a.n; k0 += CHUNK) {
+            const double u_lane = (k0 + lane < a.n) ? a.u[k0 + lane] : 0.0;
+            const int kend = (a.n - k0 < CHUNK) ? a.n - k0 : CHUNK;
+            // ring space: the publisher must have drained the chunk RING draws back
+            while (ld_acquire_smem(&flags[F_PUB]) < k0 + CHUNK - RING) __nanosleep(32);
+            for (int kk = 0; kk < kend; kk++) {
+                const int k = k0 + kk;
+                const double uk = __shfl_sync(0xffffffffu, u_lane, kk);
+                // np.random.uniform(0.0, root) = 0.0 + (root - 0.0) * u, :302
+                double pos = __dmul_rn(top[1], uk);
+                int node = older;
+                {
+                    const double left = top[older];
+                    if (!(pos < left)) {
+                        pos = __dsub_rn(pos, left);
+                        node = older ^ 1;
+                    }
+                }
+                spec_descend<T - 2, FMA>(top, node, pos, lane); // level 1 -> T-1
+                const unsigned unode = (unsigned)node;
+                // ---- the D levels under `node`: staged by the scout, or fetched here
+                const double *sub;
+                const int ready_seq = ld_acquire_smem(&flags[F_READY + (k % NBUF)]);
+                bool staged = ready_seq == k && flags[F_NODE + (k % NBUF)] == node;
+                if (ready_seq != k) late++;
+#pragma unroll
+                for (int i = 0; i < LAG; i++) staged = staged && node != prev_node[i];
+                if (staged) {
+                    sub = sub_pref + (k % NBUF) * SUBN;
+                    hits++;
+                } else {
+                    double2 tmp[NIT];
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        int q = lane + 32 * it;
+                        q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                        const int dq = 31 - __clz(q);
+                        tmp[it] =
+                            ld_tree_pair(sum2 + ((unode << dq) + (unsigned)(q - (1 << dq))), pol);
+                    }
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        int q = lane + 32 * it;
+                        q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                        reinterpret_cast<double2 *>(sub_own)[q] = tmp[it];
+                    }
+                    __syncwarp();
+                    sub = sub_own;
+                }
+                int rel = 1;
+                spec_descend<D, FMA>(sub, rel, pos, lane);
+                const unsigned leafnode = (unode << D) + (unsigned)(rel - (1 << D));
+                const double prio = sub[rel];
+                // ---- _write(ix, 0.0): re-reduce the path, siblings first (:303)
+                double sib[D + T - 1];
+#pragma unroll
+                for (int j = 0; j < D; j++) sib[j] = sub[(rel >> j) ^ 1];
+#pragma unroll
+                for (int j = 0; j < T - 1; j++) sib[D + j] = top[(node >> j) ^ 1];
+                double v = 0.0;
+                if (lane == 0) st_tree(a.sum + leafnode, 0.0, pol);
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    v = __dadd_rn(v, sib[j]);
+                    if (lane == 0) {
+                        if (j + 1 < D) {
+                            const int dp = D - j - 1; // depth of the relative parent
+                            const unsigned p = (unsigned)(rel >> (j + 1));
+                            st_tree(a.sum + ((unode << dp) + (p - (1u << dp))), v, pol);
+                        } else {
+                            top[node] = v;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < T - 1; j++) {
+                    v = __dadd_rn(v, sib[D + j]);
+                    if (lane == 0) top[node >> (j + 1)] = v;
+                }
+                if (lane == 0) {
+                    o_slot[k % RING] = (int)(leafnode - (unsigned)a.nslots);
+                    o_prio[k % RING] = prio;
+                    // publish "draws 0..k are complete" (global + shared stores above)
+                    st_release_smem(&flags[F_DONE], k + 1);
+                }
+#pragma unroll
+                for (int i = LAG - 1; i > 0; i--) prev_node[i] = prev_node[i - 1];
+                prev_node[0] = node;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) a.st->pad = hits | (late << 16); // scout diagnostics: hits, not-ready
+    } else if (warp == 3) {
+        // ----------------------------- publisher -----------------------------
+        double total = 0.0, mroot = 0.0, bmin = INFINITY;
+        const double len = (double)(a.st->napp - npop);
+        for (int k0 = 0; k0 < a.n; k0 += CHUNK) {
+            const int kend = (a.n - k0 < CHUNK) ? a.n : k0 + CHUNK;
+            while (ld_acquire_smem(&flags[F_DONE]) < kend) __nanosleep(200);
+            if (k0 == 0) {
+                total = s_stat[0];
+                mroot = s_stat[1];
+            }
+            const int k = k0 + lane;
+            if (k < kend) {
+                const long long slot = o_slot[k % RING];
+                const double prio = o_prio[k % RING];
+                a.slots_out[k] = (int32_t)slot;
+                a.prio_out[k] = prio;
+                if (a.index_out) a.index_out[k] = (slot - npop) & mask;
+                if (a.prio_user) a.prio_user[k] = prio;
+                const double p = prio / total;
+                if (a.prob) a.prob[k] = p;
+                bmin = fmin(bmin, p);
+                if (a.weight && a.norm != B2RL_NORM_BATCH)
+                    a.weight[k] = is_weight(p, mroot / total, len, a.beta, a.norm);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (a.ready) st_release_gpu(a.ready, a.seq_base | (unsigned long long)kend);
+                st_release_smem(&flags[F_PUB], kend);
+            }
+            __syncwarp();
+        }
+        if (a.weight && a.norm == B2RL_NORM_BATCH) {
+            // np.min(probabilities) over the batch, replay_buffers/prioritized.py:60
+            for (int o = 16; o > 0; o >>= 1) bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+            for (int k = lane; k < a.n; k += 32)
+                a.weight[k] = is_weight(a.prio_out[k] / total, bmin, len, a.beta, a.norm);
+        }
+    }
+    __syncthreads();
+    // publish the shared-memory levels (zeroed state) back to HBM: bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            bulk_s2g(a.sum + c * (TOPN / 4), top + c * (TOPN / 4), TOPN * 2);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// EXACT sampler, whole tree in shared memory (levels < TOP_LEVELS).  Called by
+// all threads of the CTA; warp 0 walks the draws.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void exact_small(const SampleArgs &a, double *smem_d)
+{
+    double *top = smem_d;
+    double *sub = smem_d + (1 << a.T);
+    const int topn = 1 << a.T;
+    const int tid = threadIdx.x;
+    for (int i = 1 + tid; i < topn; i += blockDim.x) top[i] = a.sum[i];
+    __syncthreads();
+
+    if (tid < 32) {
+        const int lane = tid;
+        const long long mask = a.nslots - 1;
+        const long long npop = a.st->npop;
+        // The reference's root visits its OLDER half first
+        // (collections/prioritized.py:255-258 with the bounds of :229-241).
+        const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+        const double total = top[1]; // priority_sums.sum(), :58
+        const double mroot = a.mn[1]; // priority_mins.min(), :59
+        const double len = (double)(a.st->napp - npop);
+        if (lane == 0) {
+            a.st->last_total = total;
+            a.st->last_min = mroot;
+            a.st->last_n = a.n;
+        }
+        double bmin = INFINITY;
+        double unext = a.n > 0 ? a.u[0] : 0.0;
+        for (int k = 0; k < a.n; k++) {
+            const double uk = unext;
+            if (k + 1 < a.n) unext = a.u[k + 1];
+            // np.random.uniform(0.0, root) = 0.0 + (root - 0.0) * u, :302
+            double pos = __dmul_rn(top[1], uk);
+            // _find, :245-258
+            int node = older;
+            {
+                const double left = top[older];
+                if (!(pos < left)) {
+                    pos = __dsub_rn(pos, left);
+                    node = older ^ 1;
+                }
+            }
+            for (int lv = 1; lv < a.T - 1; lv++) {
+                const double left = top[2 * node];
+                if (pos < left) {
+                    node = 2 * node;
+                } else {
+                    pos = __dsub_rn(pos, left);
+                    node = 2 * node + 1;
+                }
+            }
+            long long leafnode;
+            double prio;
+            if (a.D > 0) {
+                // one round trip: all D levels under `node`
+                for (int j = 1; j <= a.D; j++) {
+                    const int cnt = 1 << j;
+                    const double *src = a.sum + ((long long)node << j);
+                    for (int i = lane; i < cnt; i += 32) sub[cnt + i] = src[i];
+                }
+                __syncwarp();
+                int rel = 1;
+                for (int j = 0; j < a.D; j++) {
+                    const double left = sub[2 * rel];
+                    if (pos < left) {
+                        rel = 2 * rel;
+                    } else {
+                        pos = __dsub_rn(pos, left);
+                        rel = 2 * rel + 1;
+                    }
+                }
+                leafnode = ((long long)node << a.D) + (rel - (1 << a.D));
+                prio = sub[rel];
+                // _write(ix, 0.0): zero the leaf, re-reduce the path, :303
+                sub[rel] = 0.0;
+                if (lane == 0) a.sum[leafnode] = 0.0;
+                int dj = a.D - 1;
+                for (int p = rel >> 1; p >= 2; p >>= 1, dj--) {
+                    const double v = __dadd_rn(sub[2 * p], sub[2 * p + 1]);
+                    sub[p] = v;
+                    if (lane == 0) a.sum[((long long)node << dj) + (p - (1 << dj))] = v;
+                }
+                top[node] = __dadd_rn(sub[2], sub[3]);
+            } else {
+                leafnode = node;
+                prio = top[node];
+                top[node] = 0.0;
+            }
+            for (int p = node >> 1; p >= 1; p >>= 1)
+                top[p] = __dadd_rn(top[2 * p], top[2 * p + 1]);
+            if (lane == 0) {
+                const long long slot = leafnode - a.nslots;
+                a.slots_out[k] = (int32_t)slot;
+                a.prio_out[k] = prio;
+                if (a.index_out) a.index_out[k] = (slot - npop) & mask;
+                if (a.prio_user) a.prio_user[k] = prio;
+                const double p = prio / total;
+                if (a.prob) a.prob[k] = p;
+                bmin = fmin(bmin, p);
+                if (a.weight && a.norm != B2RL_NORM_BATCH)
+                    a.weight[k] = is_weight(p, mroot / total, len, a.beta, a.norm);
+                if (a.ready && ((k & 31) == 31 || k == a.n - 1))
+                    st_release_gpu(a.ready, a.seq_base | (unsigned long long)(k + 1));
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && a.weight && a.norm == B2RL_NORM_BATCH)
+            for (int k = 0; k < a.n; k++)
+                a.weight[k] = is_weight(a.prio_out[k] / total, bmin, len, a.beta, a.norm);
+    }
+    __syncthreads();
+    // publish the shared-memory levels (zeroed state) back to HBM
+    for (int i = 1 + tid; i < topn; i += blockDim.x) a.sum[i] = top[i];
+}
+
+// ---------------------------------------------------------------------------
+// PARALLEL mode: every draw descends the frozen tree on its own thread (with
+// replacement).  Three levels per global round trip: the 8 great-grandchildren
+// of a node are 64 contiguous bytes, and because every heap node is exactly
+// fl(left + right) of its children the two levels in between are recomputed
+// bit for bit from them -- the decisions are those of a level-by-level walk.
+// Called by all threads of the CTA.  red: >= 32 doubles of shared memory.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void sample_parallel(const SampleArgs &a, double *red)
+{
+    const long long mask = a.nslots - 1;
+    const long long npop = a.st->npop;
+    const double root = a.sum[1];
+    const double mroot = a.mn[1];
+    const double len = (double)(a.st->napp - npop);
+    const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+    const double older_v = a.sum[older];
+    double bmin = INFINITY;
+    for (int k = threadIdx.x; k < a.n; k += blockDim.x) {
+        double pos = __dmul_rn(root, a.u[k]);
+        long long node = older;
+        if (!(pos < older_v)) {
+            pos = __dsub_rn(pos, older_v);
+            node = older ^ 1;
+        }
+        int rem = a.levels - 1;
+        while (rem >= 3) {
+            const double2 *g = reinterpret_cast<const double2 *>(a.sum + 8 * node);
+            const double2 g01 = g[0], g23 = g[1], g45 = g[2], g67 = g[3];
+            const double c0 = __dadd_rn(g01.x, g01.y), c1 = __dadd_rn(g23.x, g23.y);
+            const double c2 = __dadd_rn(g45.x, g45.y);
+            const double l0 = __dadd_rn(c0, c1);
+            int b1 = 0, b2 = 0, b3 = 0;
+            if (!(pos < l0)) { pos = __dsub_rn(pos, l0); b1 = 1; }
+            const double l1 = b1 ? c2 : c0;
+            if (!(pos < l1)) { pos = __dsub_rn(pos, l1); b2 = 1; }
+            const double l2 = b1 ? (b2 ? g67.x : g45.x) : (b2 ? g23.x : g01.x);
+            if (!(pos < l2)) { pos = __dsub_rn(pos, l2); b3 = 1; }
+            node = 8 * node + 4 * b1 + 2 * b2 + b3;
+            rem -= 3;
+        }
+        for (; rem > 0; rem--) {
+            const double left = a.sum[2 * node];
+            if (pos < left) {
+                node = 2 * node;
+            } else {
+                pos = __dsub_rn(pos, left);
+                node = 2 * node + 1;
+            }
+        }
+        const double prio = a.sum[node];
+        const long long slot = node - a.nslots;
+        a.slots_out[k] = (int32_t)slot;
+        a.prio_out[k] = prio;
+        if (a.index_out) a.index_out[k] = (slot - npop) & mask;
+        if (a.prio_user) a.prio_user[k] = prio;
+        const double p = prio / root;
+        if (a.prob) a.prob[k] = p;
+        bmin = fmin(bmin, p);
+        if (a.weight && a.norm != B2RL_NORM_BATCH)
+            a.weight[k] = is_weight(p, mroot / root, len, a.beta, a.norm);
+    }
+    if (threadIdx.x == 0) {
+        a.st->last_total = root;
+        a.st->last_min = mroot;
+        a.st->last_n = a.n;
+    }
+    if (a.weight && a.norm == B2RL_NORM_BATCH) {
+        for (int o = 16; o > 0; o >>= 1) bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bmin;
+        __syncthreads();
+        bmin = INFINITY;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) bmin = fmin(bmin, red[w]);
+        for (int k = threadIdx.x; k < a.n; k += blockDim.x)
+            a.weight[k] = is_weight(a.prio_out[k] / root, bmin, len, a.beta, a.norm);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && a.ready) {
+        __threadfence();
+        st_release_gpu(a.ready, a.seq_base | (unsigned long long)a.n);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Priority write-back for up to UPD_MAX leaves (set_last_priority,
+// collections/prioritized.py:107-116, with priority_from_errors of
+// replay_buffers/prioritized.py:47-55 in front when TD errors are given).
+//
+// A level-synchronous walk over global memory costs one L2 round trip per
+// level (21 at 1 M capacity: 29 us for 512 leaves in round 1).  Here the
+// updated leaves are sorted, duplicates resolved (the reference writes in
+// order, so the LAST occurrence wins), and EVERY sibling any path can need is
+// fetched up front in one round trip; the level loop then runs on shared
+// memory only.  Sorted order makes the merge logic local: the paths below one
+// node form a contiguous run of entries, the first entry of a run is its
+// leader and carries the node's new value; two runs merge when they are the
+// two children of one parent.  Every parent is computed as fl(left + right) /
+// min(left, right) of its two children's final values, exactly what the
+// reference's bottom-up _write produces after the whole batch.
+// Called by all threads of the CTA.
+// ---------------------------------------------------------------------------
+static constexpr int UPD_MAX = 512;
+
+struct UpdateArgs {
+    double *sum, *mn;
+    B2rlDevState *st;
+    const int32_t *slots;
+    double *new_prio;       // [n] priorities (input, or scratch for the error form)
+    const void *err;        // optional TD errors
+    int err_is_f64;
+    double alpha, eps, emin, emax;
+    int32_t *winner;        // scratch of the level-synchronous kernel (n > UPD_MAX)
+    int n, levels;
+    long long nslots;
+};
+
+__host__ __device__ inline size_t update_paths_smem_bytes(int levels)
+{
+    // keys, leaf, runlen (int) + lead (int) + prio, vs, vm (double) + counts + siblings
+    return (size_t)UPD_MAX * (4 * 4 + 3 * 8) + 64 * 8 + (size_t)levels * UPD_MAX * 16;
+}
+
+__device__ __forceinline__ double priority_from_error(const UpdateArgs &a, int k)
+{
+    // priority_from_errors, replay_buffers/prioritized.py:47-55
+    double d = a.err_is_f64 ? ((const double *)a.err)[k] : (double)((const float *)a.err)[k];
+    if (a.emin <= a.emax) d = fmin(fmax(d, a.emin), a.emax);
+    d += a.eps;
+    return (a.alpha == 0.5) ? sqrt(d) : pow(d, a.alpha);
+}
+
+__device__ __forceinline__ void tree_update_paths(const UpdateArgs &a, unsigned char *smem_raw)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    double *prio_s = reinterpret_cast<double *>(smem_raw);      // [UPD_MAX] by draw index
+    double *vs = prio_s + UPD_MAX;                              // [UPD_MAX] by sorted entry
+    double *vm = vs + UPD_MAX;
+    double *red = vm + UPD_MAX;                                 // [64]
+    double *sib_s = red + 64;                                   // [levels][UPD_MAX]
+    double *sib_m = sib_s + (size_t)a.levels * UPD_MAX;
+    unsigned *keys = reinterpret_cast<unsigned *>(sib_m + (size_t)a.levels * UPD_MAX);
+    int *leaf = reinterpret_cast<int *>(keys + UPD_MAX);
+    int *runlen = leaf + UPD_MAX;
+    int *lead = runlen + UPD_MAX;
+    int *cnt = reinterpret_cast<int *>(red) + 64; // upper half of red[] as ints: [32..63] doubles
+
+    // ---- priorities, sort keys --------------------------------------------
+    double mx = 0.0;
+    for (int k = tid; k < UPD_MAX; k += nt) {
+        unsigned key = 0xffffffffu;
+        if (k < a.n) {
+            const double p = a.err ? priority_from_error(a, k) : a.new_prio[k];
+            if (a.err) a.new_prio[k] = p;
+            prio_s[k] = p;
+            mx = fmax(mx, p); // max_priority sees every value, :114
+            key = ((unsigned)a.slots[k] << 9) | (unsigned)k;
+        }
+        keys[k] = key;
+    }
+    __syncthreads();
+    // ---- bitonic sort of (slot, draw index) --------------------------------
+    for (int kk = 2; kk <= UPD_MAX; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < UPD_MAX; i += nt) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned x = keys[i], y = keys[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((x > y) == up) {
+                        keys[i] = y;
+                        keys[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- unique leaves (last occurrence of a slot wins), compaction ---------
+    // groups of 32 consecutive entries: ballot + popc, then a prefix over the
+    // <= 16 group counts
+    for (int g = warp; g < UPD_MAX / 32; g += nw) {
+        const int i = g * 32 + lane;
+        const bool w = i < a.n && (i == a.n - 1 || (keys[i + 1] >> 9) != (keys[i] >> 9));
+        const unsigned b = __ballot_sync(0xffffffffu, w);
+        if (lane == 0) cnt[g] = __popc(b);
+    }
+    __syncthreads();
+    int m = 0;
+    for (int g = 0; g < UPD_MAX / 32; g++) m += cnt[g];
+    for (int g = warp; g < UPD_MAX / 32; g += nw) {
+        const int i = g * 32 + lane;
+        const bool w = i < a.n && (i == a.n - 1 || (keys[i + 1] >> 9) != (keys[i] >> 9));
+        const unsigned b = __ballot_sync(0xffffffffu, w);
+        int base = 0;
+        for (int q = 0; q < g; q++) base += cnt[q];
+        if (w) {
+            const int pos = base + __popc(b & ((1u << lane) - 1u));
+            const int slot = (int)(keys[i] >> 9);
+            const double p = prio_s[keys[i] & 511u];
+            leaf[pos] = slot;
+            vs[pos] = p;
+            vm[pos] = p;
+            runlen[pos] = 1;
+            lead[pos] = 1;
+        }
+    }
+    __syncthreads();
+    // ---- leaves out, every sibling of every path in (one round trip) --------
+    for (int i = tid; i < m; i += nt) {
+        const long long ln = a.nslots + leaf[i];
+        a.sum[ln] = vs[i];
+        a.mn[ln] = vm[i];
+    }
+    for (int idx = tid; idx < m * a.levels; idx += nt) {
+        const int i = idx % m, s = idx / m; // s = sh - 1
+        const long long node = (a.nslots + leaf[i]) >> s;
+        sib_s[(size_t)s * UPD_MAX + i] = a.sum[node ^ 1];
+        sib_m[(size_t)s * UPD_MAX + i] = a.mn[node ^ 1];
+    }
+    __syncthreads();
+    // ---- level loop on shared memory ----------------------------------------
+    for (int s = 0; s < a.levels; s++) {
+        for (int i = tid; i < m; i += nt) {
+            if (!lead[i]) continue;
+            const long long node = (a.nslots + leaf[i]) >> s;
+            double ns, nm;
+            if ((node & 1) == 0) {
+                const int j = i + runlen[i];
+                if (j < m && ((a.nslots + leaf[j]) >> s) == node + 1) {
+                    ns = __dadd_rn(vs[i], vs[j]);
+                    nm = fmin(vm[i], vm[j]);
+                    runlen[i] += runlen[j];
+                } else {
+                    ns = __dadd_rn(vs[i], sib_s[(size_t)s * UPD_MAX + i]);
+                    nm = fmin(vm[i], sib_m[(size_t)s * UPD_MAX + i]);
+                }
+            } else {
+                if (i > 0 && ((a.nslots + leaf[i - 1]) >> s) == node - 1) {
+                    lead[i] = 0; // merged into the run on the left by its leader
+                    continue;
+                }
+                ns = __dadd_rn(sib_s[(size_t)s * UPD_MAX + i], vs[i]);
+                nm = fmin(sib_m[(size_t)s * UPD_MAX + i], vm[i]);
+            }
+            vs[i] = ns;
+            vm[i] = nm;
+            a.sum[node >> 1] = ns;
+            a.mn[node >> 1] = nm;
+        }
+        __syncthreads();
+    }
+    // ---- max_priority, :114 ---------------------------------------------------
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nw; w++) mx = fmax(mx, red[w]);
+        if (mx > a.st->max_priority) a.st->max_priority = mx;
+        a.st->last_n = 0;
+    }
+    __syncthreads();
+}

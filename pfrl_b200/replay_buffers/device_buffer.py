@@ -118,6 +118,10 @@ class DeviceExperiences(collections.abc.Sequence):
         self.weights = weights  # CUDA f32 or None
         self.pending = pending  # gather through the handle's last sampled slots
         self._lists = None
+        # fused step: the raw gather outputs that came out of the same launch as
+        # the draws, and the (gamma, obs_mode, obs_scale) they were made for
+        self._prefetched = None
+        self._prefetch_key = None
 
     def __len__(self):
         return self.n
@@ -431,17 +435,32 @@ class DeviceNStepBuffer:
         common = dict(index=index, action_dtype=lay.torch_action_dtype(),
                       action_shape=lay.action_shape, want_steps=want_steps)
         gp = self._gamma_pow(gamma)
+        key = self._plan_key(gamma, phi, raw)
+        pre = None
+        if not want_steps and exps._prefetched is not None and exps._prefetch_key == key:
+            pre = dict(exps._prefetched)  # outputs of the fused step launch
+        elif self._prioritized and exps.pending and not want_steps and not raw:
+            # remember what the agent asks for: the next sample() gathers in the
+            # same launch as it draws (b2rl_replay_step)
+            self._plan = (key, gamma, phi, raw)
         if mode == _lib.OBS_U8_TO_F32:
             assert lay.torch_obs_dtype() == torch.uint8
             padded = lay.part_nbytes != lay.part_bytes
-            out = self.store.gather(exps.n, gp, obs_mode=mode, obs_scale=phi.b2rl_obs_scale,
-                                    obs_shape=None if padded else lay.obs_shape, **common)
+            if pre is not None:
+                out = pre
+                if not padded:
+                    for k in ("state", "next_state"):
+                        out[k] = out[k].view((exps.n,) + tuple(lay.obs_shape))
+            else:
+                out = self.store.gather(exps.n, gp, obs_mode=mode, obs_scale=phi.b2rl_obs_scale,
+                                        obs_shape=None if padded else lay.obs_shape, **common)
             if padded:  # parts are padded to 16 B in the ring: drop the pad columns
                 for k in ("state", "next_state"):
                     t = out[k].view(exps.n, lay.stack, lay.part_bytes)[:, :, :lay.part_nbytes]
                     out[k] = t.contiguous().view((exps.n,) + tuple(lay.obs_shape))
         else:
-            out = self.store.gather(exps.n, gp, obs_mode=_lib.OBS_RAW, **common)
+            out = pre if pre is not None else self.store.gather(
+                exps.n, gp, obs_mode=_lib.OBS_RAW, **common)
             for k in ("state", "next_state"):
                 t = out[k]  # [n, stack * part_bytes] uint8
                 if lay.part_nbytes != lay.part_bytes:
@@ -459,6 +478,13 @@ class DeviceNStepBuffer:
         if exps.weights is not None:
             out["weights"] = exps.weights
         return out
+
+    @staticmethod
+    def _plan_key(gamma, phi, raw):
+        mode = None if raw else getattr(phi, "b2rl_obs_mode", None)
+        if mode == _lib.OBS_U8_TO_F32:
+            return (float(gamma), int(mode), float(phi.b2rl_obs_scale))
+        return (float(gamma), int(_lib.OBS_RAW), 1.0)
 
     def _materialise(self, exps):
         out = self._gather(exps, 1.0, None, raw=True, want_steps=True)
@@ -562,7 +588,7 @@ class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
     def __init__(self, capacity=None, alpha=0.6, beta0=0.4, betasteps=2e5, eps=0.01,
                  normalize_by_max=True, error_min=0, error_max=1, num_steps=1, *,
                  device=None, part_capacity=None, max_batch=4096, sample_mode="exact",
-                 unbounded_capacity=_UNBOUNDED_DEFAULT):
+                 unbounded_capacity=_UNBOUNDED_DEFAULT, fused=True):
         DeviceNStepBuffer.__init__(self, capacity, num_steps, device=device,
                                    part_capacity=part_capacity, max_batch=max_batch,
                                    unbounded_capacity=unbounded_capacity)
@@ -571,6 +597,12 @@ class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
         assert sample_mode in ("exact", "parallel")
         self.sample_mode = sample_mode
         self._waiting = False
+        # fused=True: once batch_experiences has been seen with a device-side phi,
+        # sample() draws, weighs and gathers in ONE launch (b2rl_replay_step) and a
+        # CUDA-tensor update_errors() is folded into the head of the next one.  The
+        # results are those of the separate calls (tests/test_fused_step_gpu.py).
+        self.fused = fused
+        self._plan = None
 
     def sample(self, n):
         assert len(self) >= n
@@ -581,14 +613,26 @@ class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
         # consumes exactly random_sample() (collections/prioritized.py:302)
         u = np.random.random_sample(n)
         mode = _lib.SAMPLE_EXACT if self.sample_mode == "exact" else _lib.SAMPLE_PARALLEL
-        index, _ = self.store.sample(u, mode=mode, want_priority=False)
         norm = {False: _lib.NORM_NONE, "batch": _lib.NORM_BATCH, "memory": _lib.NORM_MEMORY}[
             self.normalize_by_max]
-        weights = self.store.weights(n, self.beta, norm)
+        pre = key = None
+        if self.fused and self._plan is not None and hasattr(self.store, "step"):
+            key, gamma, phi, raw = self._plan
+            lay = self.layout
+            pre = self.store.step(
+                u, self._gamma_pow(gamma), self.beta, norm, mode=mode, obs_mode=key[1],
+                obs_scale=key[2], action_dtype=lay.torch_action_dtype(),
+                action_shape=lay.action_shape)
+            index, weights = pre.pop("index"), pre.pop("weights")
+        else:
+            index, _ = self.store.sample(u, mode=mode, want_priority=False)
+            weights = self.store.weights(n, self.beta, norm)
         self.beta = min(1.0, self.beta + self.beta_add)  # prioritized.py:65
         self._waiting = True
         self._last_n = n
         self._last_handle = DeviceExperiences(self, n, index=index, weights=weights, pending=True)
+        self._last_handle._prefetched = pre
+        self._last_handle._prefetch_key = key
         return self._last_handle
 
     def update_errors(self, errors):
@@ -603,8 +647,14 @@ class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
             e = errors.detach()
             if e.dtype not in (torch.float32, torch.float64):
                 e = e.float()
-            self.store.update_errors(e.contiguous().view(-1), self.alpha, self.eps,
-                                     self.error_min, self.error_max)
+            if self.fused and self._plan is not None and hasattr(self.store, "defer_errors"):
+                # no launch: folded into the head of the next fused step (or applied
+                # before the next append / tree access, whichever comes first)
+                self.store.defer_errors(e.contiguous().view(-1), self.alpha, self.eps,
+                                        self.error_min, self.error_max)
+            else:
+                self.store.update_errors(e.contiguous().view(-1), self.alpha, self.eps,
+                                         self.error_min, self.error_max)
         else:
             if isinstance(errors, torch.Tensor):
                 errors = errors.tolist()

@@ -19,8 +19,8 @@ def _np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class DeviceReplayStore:
@@ -84,13 +84,13 @@ class DeviceReplayStore:
             n = parts.numel() * parts.element_size() // self.part_bytes
             slots = np.empty(n, dtype=np.int32)
             _lib.check(self.L.b2rl_replay_put_parts(
-                self.h, ctypes.c_void_p(parts.data_ptr()), 1, n, _np_ptr(slots), _stream()))
+                self.h, ctypes.c_void_p(parts.data_ptr()), 1, n, _np_ptr(slots), _stream(self.device)))
             return slots
         a = np.ascontiguousarray(parts)
         n = a.nbytes // self.part_bytes
         assert n * self.part_bytes == a.nbytes
         slots = np.empty(n, dtype=np.int32)
-        _lib.check(self.L.b2rl_replay_put_parts(self.h, _np_ptr(a), 0, n, _np_ptr(slots), _stream()))
+        _lib.check(self.L.b2rl_replay_put_parts(self.h, _np_ptr(a), 0, n, _np_ptr(slots), _stream(self.device)))
         return slots
 
     # -- append ------------------------------------------------------------
@@ -112,7 +112,7 @@ class DeviceReplayStore:
             rewards=rw.ctypes.data, len=ln.ctypes.data, terminal=tm.ctypes.data,
             priority=None if pr is None else pr.ctypes.data,
         )
-        _lib.check(self.L.b2rl_replay_append(self.h, ctypes.byref(e), n, 0, _stream()))
+        _lib.check(self.L.b2rl_replay_append(self.h, ctypes.byref(e), n, 0, _stream(self.device)))
 
     # -- prioritized sampling ------------------------------------------------
     def sample(self, u, mode=SAMPLE_EXACT, want_index=True, want_priority=True):
@@ -123,7 +123,7 @@ class DeviceReplayStore:
         _lib.check(self.L.b2rl_per_sample(
             self.h, _np_ptr(u), n, mode,
             ctypes.c_void_p(idx.data_ptr()) if want_index else None,
-            ctypes.c_void_p(pri.data_ptr()) if want_priority else None, _stream()))
+            ctypes.c_void_p(pri.data_ptr()) if want_priority else None, _stream(self.device)))
         return idx, pri
 
     def weights(self, n, beta, norm, want_prob=False):
@@ -131,17 +131,17 @@ class DeviceReplayStore:
         p = torch.empty(n, dtype=torch.float64, device=self.device) if want_prob else None
         _lib.check(self.L.b2rl_per_weights(
             self.h, float(beta), int(norm), ctypes.c_void_p(w.data_ptr()),
-            ctypes.c_void_p(p.data_ptr()) if want_prob else None, _stream()))
+            ctypes.c_void_p(p.data_ptr()) if want_prob else None, _stream(self.device)))
         return (w, p) if want_prob else w
 
     def update_priorities(self, priority):
         if isinstance(priority, torch.Tensor):
             assert priority.is_cuda and priority.dtype == torch.float64 and priority.is_contiguous()
             _lib.check(self.L.b2rl_per_update_priorities(
-                self.h, ctypes.c_void_p(priority.data_ptr()), 1, priority.numel(), _stream()))
+                self.h, ctypes.c_void_p(priority.data_ptr()), 1, priority.numel(), _stream(self.device)))
         else:
             p = np.ascontiguousarray(priority, dtype=np.float64)
-            _lib.check(self.L.b2rl_per_update_priorities(self.h, _np_ptr(p), 0, p.shape[0], _stream()))
+            _lib.check(self.L.b2rl_per_update_priorities(self.h, _np_ptr(p), 0, p.shape[0], _stream(self.device)))
 
     def update_errors(self, errors, alpha, eps, error_min, error_max):
         assert isinstance(errors, torch.Tensor) and errors.is_cuda and errors.is_contiguous()
@@ -155,22 +155,103 @@ class DeviceReplayStore:
         _lib.check(self.L.b2rl_per_update_errors(
             self.h, ctypes.c_void_p(errors.data_ptr()), int(errors.dtype == torch.float64),
             errors.numel(), float(alpha), float(eps), float(error_min), float(error_max),
-            _stream()))
+            _stream(self.device)))
+
+    def defer_errors(self, errors, alpha, eps, error_min, error_max):
+        """Answer the last sample without a launch: the write-back runs at the
+        head of the next fused step (or before the next tree access).  The
+        tensor is kept alive until then."""
+        assert isinstance(errors, torch.Tensor) and errors.is_cuda and errors.is_contiguous()
+        assert errors.dtype in (torch.float32, torch.float64)
+        if error_min is None and error_max is None:
+            error_min, error_max = 1.0, 0.0  # min > max disables clipping
+        elif error_min is None:
+            error_min = -float("inf")
+        elif error_max is None:
+            error_max = float("inf")
+        _lib.check(self.L.b2rl_per_defer_errors(
+            self.h, ctypes.c_void_p(errors.data_ptr()), int(errors.dtype == torch.float64),
+            errors.numel(), float(alpha), float(eps), float(error_min), float(error_max)))
+        self._deferred_errors = errors
+
+    def flush(self):
+        _lib.check(self.L.b2rl_per_flush(self.h, _stream(self.device)))
+        self._deferred_errors = None
+
+    def step(self, u, gamma_pow, beta, norm, mode=SAMPLE_EXACT, obs_mode=OBS_RAW,
+             obs_scale=1.0, obs_dtype=None, obs_shape=None, action_dtype=torch.int64,
+             action_shape=(), want_obs=True, want_index=True, want_priority=False,
+             want_prob=False, out=None):
+        """Fused replay step (b2rl_replay_step): [deferred write-back] -> sample ->
+        importance weights -> gather, one launch.  u: numpy float64 [n] (host) or a
+        CUDA float64 tensor.  Returns (batch dict, index, weights[, priority, prob]).
+        `out`: dict of preallocated output tensors from an earlier call (reused)."""
+        n = int(u.shape[0])
+        dev = self.device
+        gp = np.ascontiguousarray(gamma_pow, dtype=np.float64)
+        assert gp.shape[0] == self.n_step + 1
+        obs_bytes = self.stack * self.part_bytes
+        if out is None:
+            out = {}
+            if want_obs:
+                if obs_mode == OBS_U8_TO_F32:
+                    odt, oshape = torch.float32, (n, obs_bytes)
+                else:
+                    odt = obs_dtype or torch.uint8
+                    oshape = (n, obs_bytes // torch.empty((), dtype=odt).element_size())
+                out["state"] = torch.empty(oshape, dtype=odt, device=dev)
+                out["next_state"] = torch.empty(oshape, dtype=odt, device=dev)
+            asz = torch.empty((), dtype=action_dtype).element_size()
+            out["action"] = torch.empty((n, self.action_bytes // asz), dtype=action_dtype, device=dev)
+            out["reward"] = torch.empty(n, dtype=torch.float32, device=dev)
+            out["is_state_terminal"] = torch.empty(n, dtype=torch.float32, device=dev)
+            out["discount"] = torch.empty(n, dtype=torch.float32, device=dev)
+            out["weights"] = torch.empty(n, dtype=torch.float32, device=dev)
+            if want_index:
+                out["index"] = torch.empty(n, dtype=torch.int64, device=dev)
+            if want_priority:
+                out["priority"] = torch.empty(n, dtype=torch.float64, device=dev)
+            if want_prob:
+                out["prob"] = torch.empty(n, dtype=torch.float64, device=dev)
+        ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
+        if isinstance(u, torch.Tensor):
+            assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous()
+            u_ptr, u_dev, keep = u.data_ptr(), 1, u
+        else:
+            keep = np.ascontiguousarray(u, dtype=np.float64)
+            u_ptr, u_dev = keep.ctypes.data, 0
+        a = _lib.StepArgs(
+            n=n, mode=int(mode), u=u_ptr, u_on_device=u_dev, norm=int(norm), beta=float(beta),
+            gamma_pow_host=gp.ctypes.data, obs_mode=int(obs_mode), obs_scale=float(obs_scale),
+            index_dev=ptr("index"), priority_dev=ptr("priority"), weight_dev=ptr("weights"),
+            prob_dev=ptr("prob"),
+            out=_lib.BatchOut(
+                state=ptr("state"), next_state=ptr("next_state"), action=ptr("action"),
+                reward=ptr("reward"), terminal=ptr("is_state_terminal"),
+                discount=ptr("discount"), step_rewards=None, len=None))
+        _lib.check(self.L.b2rl_replay_step(self.h, ctypes.byref(a), _stream(self.device)))
+        self._deferred_errors = None  # consumed by the launch (stream-ordered)
+        res = dict(out)
+        if want_obs and obs_shape is not None:
+            res["state"] = res["state"].view((n,) + tuple(obs_shape))
+            res["next_state"] = res["next_state"].view((n,) + tuple(obs_shape))
+        res["action"] = res["action"].view((n,) + tuple(action_shape))
+        return res
 
     def info(self):
         out = _lib.PerInfo()
-        _lib.check(self.L.b2rl_per_get_info(self.h, ctypes.byref(out), _stream()))
+        _lib.check(self.L.b2rl_per_get_info(self.h, ctypes.byref(out), _stream(self.device)))
         return dict(total=out.total, min=out.min, max_priority=out.max_priority,
                     napp=out.napp, npop=out.npop, scout_hits=out.scout_hits)
 
     def set_max_priority(self, value):
-        _lib.check(self.L.b2rl_per_set_max_priority(self.h, float(value), _stream()))
+        _lib.check(self.L.b2rl_per_set_max_priority(self.h, float(value), _stream(self.device)))
 
     def read_priorities(self, first=0, n=None):
         if n is None:
             n = len(self) - first
         out = np.empty(n, dtype=np.float64)
-        _lib.check(self.L.b2rl_per_read_priorities(self.h, first, n, _np_ptr(out), _stream()))
+        _lib.check(self.L.b2rl_per_read_priorities(self.h, first, n, _np_ptr(out), _stream(self.device)))
         return out
 
     # -- gather --------------------------------------------------------------
@@ -210,7 +291,7 @@ class DeviceReplayStore:
         )
         _lib.check(self.L.b2rl_replay_gather(
             self.h, ctypes.c_void_p(index.data_ptr()) if index is not None else None, n,
-            _np_ptr(gp), int(obs_mode), float(obs_scale), ctypes.byref(bo), _stream()))
+            _np_ptr(gp), int(obs_mode), float(obs_scale), ctypes.byref(bo), _stream(self.device)))
         if want_obs and obs_shape is not None:
             out["state"] = out["state"].view((n,) + tuple(obs_shape))
             out["next_state"] = out["next_state"].view((n,) + tuple(obs_shape))
