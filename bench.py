@@ -61,6 +61,8 @@ ALGO_BYTES_GATHER = 7 * FRAME_BYTES + 2 * STACK * FRAME_BYTES * 4 + 32
 # ... + tree traffic of the draw and of the write-back (~1.7 KB) = 276.9 KB
 ALGO_BYTES_TREE = 1684
 ALGO_BYTES_PATH = ALGO_BYTES_GATHER + ALGO_BYTES_TREE
+# uint8 batches out (x/255 folded into conv1): 7 frames read + 2 x 4 frames written = 107.6 KB
+ALGO_BYTES_PATH_U8 = 7 * FRAME_BYTES + 2 * STACK * FRAME_BYTES + 32 + ALGO_BYTES_TREE
 
 
 def parse():
@@ -455,10 +457,10 @@ def main():
     h = store.h
     beta, scale = float(buf.beta), float(phi.b2rl_obs_scale)
 
-    def fused_loop(mode):
+    def fused_loop(mode, obs_mode=_lib.OBS_U8_TO_F32, K=K, W=W):
         sa = _lib.StepArgs(
             n=B, mode=mode, u=u_dev.data_ptr(), u_on_device=1, norm=_lib.NORM_MEMORY, beta=beta,
-            gamma_pow_host=gp_arr.ctypes.data, obs_mode=_lib.OBS_U8_TO_F32, obs_scale=scale,
+            gamma_pow_host=gp_arr.ctypes.data, obs_mode=obs_mode, obs_scale=scale,
             index_dev=o_index.data_ptr(), priority_dev=None, weight_dev=o_weight.data_ptr(),
             prob_dev=None, out=batch_out)
         sa_ref = ctypes.byref(sa)
@@ -483,15 +485,23 @@ def main():
             one_pass()
         t1.record()
         barrier()
+        ph = (ctypes.c_uint64 * 4)()
+        _lib.check(L.b2rl_step_times(h, ph, stream))  # %globaltimer stamps of the last launch
         _lib.check(L.b2rl_per_flush(h, stream))
-        return t0.elapsed_time(t1)
+        return t0.elapsed_time(t1), {"write_back_us": ph[0] / 1e3, "sampling_us": ph[1] / 1e3,
+                                     "gather_after_last_draw_us": ph[2] / 1e3,
+                                     "launch_us": ph[3] / 1e3}
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()  # samples SM clock / throttle reasons through all timed regions
-    ms_value = fused_loop(_lib.SAMPLE_EXACT)
+    ms_value, phases_exact = fused_loop(_lib.SAMPLE_EXACT)
     scout = store.info()["scout_hits"]
-    ms_par = fused_loop(_lib.SAMPLE_PARALLEL)
+    ms_par, phases_par = fused_loop(_lib.SAMPLE_PARALLEL)
+    # the same pass emitting uint8 batches (x/255 folded into the first conv layer): the
+    # f32 output tensors are simply reused as byte buffers
+    K8 = max(2, K // 4)
+    ms_par_u8, phases_par_u8 = fused_loop(_lib.SAMPLE_PARALLEL, _lib.OBS_RAW, K=K8, W=1)
 
     # ---- stand-alone kernels (sub-records of the roofline): event pairs around each
     kern = {"sample_exact": [], "sample_parallel": [], "weights": [], "gather": [], "update": []}
@@ -653,17 +663,28 @@ def main():
                          traffic=ncu_traffic("step_exact") if full else None,
                          dominant_phase="exact sampler (dependent chain of %d draws)" % B,
                          traffic_source="profiles/r*_ncu_full_summary.csv (ncu --set full, per launch)",
-                         algorithmic_bytes_per_sample=ALGO_BYTES_PATH, kernels=sub),
+                         algorithmic_bytes_per_sample=ALGO_BYTES_PATH,
+                         phases_of_one_launch=phases_exact, kernels=sub),
         "sampler": {"mode": "exact", "ns_per_draw_fused_pass": 1e6 * ms_pass / B,
+                    "ns_per_draw_sampling_phase": 1e3 * phases_exact["sampling_us"] / B,
                     "ns_per_draw_kernel": 1e6 * kern_ms["sample_exact"] / B,
-                    "scout_prefetch_hits": scout & 0xffff, "scout_not_ready": scout >> 16},
+                    "fast_draws": scout & 0xffff, "slow_draws": scout >> 16},
         "throughput_mode": {
             "sampler": "parallel (all descents concurrent on the frozen tree, with replacement; "
                        "not index-identical to the reference)",
             "value": value_par, "unit": "samples/s", "ms_per_pass": ms_pass_par,
             "gpu_launches": K * R,
             "roofline": roof(ALGO_BYTES_PATH * B, ms_pass_par, "k_replay_step<parallel>",
-                             traffic=ncu_traffic("step_parallel") if full else None)},
+                             traffic=ncu_traffic("step_parallel") if full else None,
+                             phases_of_one_launch=phases_par),
+            "u8_out": {
+                "note": "same pass, uint8 state / next_state out (SURVEY 8(d): 107.6 KB/sample); "
+                        "rank 0 only, not part of `value`",
+                "ms_per_pass": ms_par_u8 / (K8 * R),
+                "samples_per_sec_per_gpu": B * K8 * R / (ms_par_u8 / 1e3),
+                "roofline": roof(ALGO_BYTES_PATH_U8 * B, ms_par_u8 / (K8 * R),
+                                 "k_replay_step<parallel, u8 out>",
+                                 phases_of_one_launch=phases_par_u8)}},
         "separate_launches_ms": kern_ms,
         "clocks": clk, "prefill_s": fill_s,
         "hbm_bytes_per_rank": store.device_bytes,

@@ -258,6 +258,12 @@ typedef struct {
 
 int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *args, void *stream);
 
+/* Phase durations (ns) of the last b2rl_replay_step launch, from timestamps the
+ * kernel leaves behind (synchronises `stream`): out_ns[0] deferred write-back,
+ * [1] sampling (until the last draw is published), [2] gather tail (from there to the
+ * exit of the last CTA), [3] the whole launch.  Measurement aid (bench.py). */
+int b2rl_step_times(b2rl_replay *h, uint64_t *out_ns_host, void *stream);
+
 /* Answer the last sample with TD errors on the device WITHOUT launching: the
  * write-back runs at the head of the next b2rl_replay_step launch, or before
  * the next call that reads or writes the trees (append, sample, get_info, ...),
@@ -347,6 +353,34 @@ int b2rl_ppo_loss(const float *log_prob, const float *entropy,
                   float *g_v_pred, double *scratch, float *losses, void *stream);
 
 /* ------------------------------------------------------------------------
+ * SAC / TD3 / DDPG update tail (fp32, device pointers).
+ * ---------------------------------------------------------------------- */
+
+/* Polyak averaging of up to any number of (target, source) fp32 tensor pairs in
+ * one launch per 96 pairs: target = target * float(1 - tau) + float(tau) * source,
+ * each operation rounded separately -- bit for bit soft_copy_param's
+ * `target.mul_(1 - tau); target.add_(tau * source)` (pfrl/utils/copy_param.py:9-22,
+ * called from SoftActorCritic.sync_target_network, soft_actor_critic.py:199-212).
+ * pairs_host is read before the call returns. */
+typedef struct {
+    void *dst;       /* target tensor (device, fp32, contiguous) */
+    const void *src; /* source tensor (device, fp32, contiguous) */
+    int64_t numel;
+} b2rl_tensor_pair;
+int b2rl_polyak(const b2rl_tensor_pair *pairs_host, int32_t n_pairs, double tau,
+                void *stream);
+
+/* Entropy-regularised TD target of SoftActorCritic.update_q_func
+ * (pfrl/agents/soft_actor_critic.py:225-240):
+ *   out = reward + discount * (1 - terminal) * (min(q1, q2) - temperature * log_prob)
+ * with the reference's operation order and one rounding per operation.
+ * temperature_dev (device scalar) takes precedence over `temperature`. */
+int b2rl_sac_target(const float *reward, const float *discount, const float *terminal,
+                    const float *q1, const float *q2, const float *log_prob,
+                    const float *temperature_dev, float temperature, int32_t n,
+                    float *out, void *stream);
+
+/* ------------------------------------------------------------------------
  * Dense contraction kept in exact fp32: first Nature-DQN convolution,
  * x[N,4,84,84] * w[32,4,8,8] (stride 4) + bias -> out[N,32,20,20].
  * Replaces the cuDNN call behind nn.Conv2d(4, 32, 8, stride=4)
@@ -354,6 +388,14 @@ int b2rl_ppo_loss(const float *log_prob, const float *entropy,
  * in the forward direction; bias may be NULL. */
 int b2rl_conv_nature1_fwd(const float *x, const float *w, const float *bias,
                           int32_t n_images, float *out, void *stream);
+/* Same layer on uint8 images x[N,4,84,84] (what b2rl_replay_gather / b2rl_replay_step
+ * emit with B2RL_OBS_RAW): the kernel expands float(x) * scale in shared memory, i.e.
+ * phi = x / 255 (examples/atari/train_dqn_batch_ale.py:229-231) is folded into the
+ * convolution and the f32 batch never exists in HBM.  Bit-identical to
+ * b2rl_conv_nature1_fwd on the B2RL_OBS_U8_TO_F32 output for the same scale. */
+int b2rl_conv_nature1_fwd_u8(const uint8_t *x, float scale, const float *w,
+                             const float *bias, int32_t n_images, float *out,
+                             void *stream);
 
 #ifdef __cplusplus
 }

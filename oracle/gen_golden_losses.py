@@ -392,7 +392,7 @@ def agent_traces(out_dir):
 MORE_TRACE_KINDS = ("iqn", "sac", "td3", "ddpg", "ppo")
 
 
-def _make_more_agent(lib, kind, rbuf):
+def _make_more_agent(lib, kind, rbuf, gpu=None):
     import torch
     from torch import distributions, nn
 
@@ -420,7 +420,7 @@ def _make_more_agent(lib, kind, rbuf):
         return lib.agents.IQN(
             q, adam(q), rbuf, 0.95, eps, replay_start_size=40, minibatch_size=16,
             update_interval=1, target_update_interval=20, phi=phi,
-            quantile_thresholds_N=6, quantile_thresholds_N_prime=5, quantile_thresholds_K=4)
+            quantile_thresholds_N=6, quantile_thresholds_N_prime=5, quantile_thresholds_K=4, gpu=gpu)
     if kind == "sac":
         def squashed(x):
             mean, log_scale = torch.chunk(x, 2, dim=1)
@@ -435,19 +435,19 @@ def _make_more_agent(lib, kind, rbuf):
         return lib.agents.SoftActorCritic(
             policy, q1, q2, adam(policy), adam(q1), adam(q2), rbuf, gamma=0.95,
             replay_start_size=40, minibatch_size=16, entropy_target=-1.0,
-            temperature_optimizer_lr=3e-3, phi=phi, burnin_action_func=burn)
+            temperature_optimizer_lr=3e-3, phi=phi, burnin_action_func=burn, gpu=gpu)
     ex = lib.explorers.AdditiveGaussian(scale=0.3, low=-1, high=1)
     if kind == "td3":
         p, q1, q2 = det_policy(), qf(), qf()
         return lib.agents.TD3(p, q1, q2, adam(p), adam(q1), adam(q2), rbuf, 0.95, ex,
                               replay_start_size=40, minibatch_size=16, phi=phi,
-                              burnin_action_func=burn)
+                              burnin_action_func=burn, gpu=gpu)
     if kind == "ddpg":
         p, q = det_policy(), qf()
         return lib.agents.DDPG(p, q, adam(p), adam(q), rbuf, 0.95, ex, replay_start_size=40,
                                minibatch_size=16, phi=phi, target_update_method="soft",
                                target_update_interval=1, soft_update_tau=0.05,
-                               burnin_action_func=burn)
+                               burnin_action_func=burn, gpu=gpu)
     if kind == "ppo":
         model = nn.Sequential(nn.Linear(5, 32), nn.Tanh(), lib.nn.Branched(
             nn.Sequential(nn.Linear(32, 2), lib.policies.SoftmaxCategoricalHead()),
@@ -456,7 +456,7 @@ def _make_more_agent(lib, kind, rbuf):
             model, torch.optim.Adam(model.parameters(), lr=3e-3),
             obs_normalizer=lib.nn.EmpiricalNormalization(5, clip_threshold=5), gamma=0.95,
             lambd=0.9, phi=phi, update_interval=64, minibatch_size=16, epochs=3, clip_eps=0.2,
-            clip_eps_vf=0.3, entropy_coef=0.01, max_grad_norm=0.5)
+            clip_eps_vf=0.3, entropy_coef=0.01, max_grad_norm=0.5, gpu=gpu)
     raise ValueError(kind)
 
 

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libb2rl.so")
-SOURCES = ["replay.cu", "sampler.cu", "step.cu", "gather.cu", "losses.cu", "ppo.cu", "conv.cu"]
+SOURCES = ["replay.cu", "sampler.cu", "step.cu", "gather.cu", "losses.cu", "ppo.cu", "sac.cu", "conv.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -113,6 +113,10 @@ class StepArgs(ctypes.Structure):
     ]
 
 
+class TensorPair(ctypes.Structure):
+    _fields_ = [("dst", ctypes.c_void_p), ("src", ctypes.c_void_p), ("numel", ctypes.c_int64)]
+
+
 class PerInfo(ctypes.Structure):
     _fields_ = [
         ("total", ctypes.c_double),
@@ -153,6 +157,7 @@ SIGNATURES = {
     "b2rl_per_read_priorities": (_int, [_vp, _i64, _i64, _vp, _vp]),
     "b2rl_per_set_max_priority": (_int, [_vp, _dbl, _vp]),
     "b2rl_replay_step": (_int, [_vp, ctypes.POINTER(StepArgs), _vp]),
+    "b2rl_step_times": (_int, [_vp, _vp, _vp]),
     "b2rl_per_defer_errors": (_int, [_vp, _vp, _int, _i32, _dbl, _dbl, _dbl, _dbl]),
     "b2rl_per_flush": (_int, [_vp, _vp]),
     "b2rl_replay_gather": (
@@ -165,7 +170,10 @@ SIGNATURES = {
     "b2rl_quantile_huber_bwd": (_int, [_vp] * 5 + [_i32, _i32, _i32, _int, _vp, _vp]),
     "b2rl_gae": (_int, [_vp] * 6 + [_i32, _i32, _dbl, _dbl] + [_vp] * 5),
     "b2rl_ppo_loss": (_int, [_vp] * 8 + [_i32] + [ctypes.c_float] * 4 + [_vp] * 6),
+    "b2rl_polyak": (_int, [ctypes.POINTER(TensorPair), _i32, _dbl, _vp]),
+    "b2rl_sac_target": (_int, [_vp] * 7 + [ctypes.c_float, _i32, _vp, _vp]),
     "b2rl_conv_nature1_fwd": (_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "b2rl_conv_nature1_fwd_u8": (_int, [_vp, ctypes.c_float, _vp, _vp, _i32, _vp, _vp]),
 }
 
 _lib = None

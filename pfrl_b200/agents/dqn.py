@@ -84,8 +84,10 @@ class _DeviceRing:
         if self.buf is None:
             self.buf = torch.zeros(self.maxlen, device=v.device)
         if v.numel() >= self.maxlen:
+            # the whole window is replaced: restart the ring at slot 0 so that the next
+            # write overwrites the OLDEST value (count stays a multiple of maxlen)
             self.buf.copy_(v[-self.maxlen:])
-            self.count += v.numel()
+            self.count = (self.count // self.maxlen + 2) * self.maxlen
             return
         pos = self.count % self.maxlen
         first = min(v.numel(), self.maxlen - pos)
@@ -152,6 +154,7 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
             episodic_update=False, episodic_update_len=episodic_update_len,
             n_times_update=n_times_update, replay_start_size=replay_start_size,
             update_interval=update_interval)
+        self.replay_updater.agent = self
         self.minibatch_size = minibatch_size
         self.episodic_update_len = episodic_update_len
         self.replay_start_size = replay_start_size

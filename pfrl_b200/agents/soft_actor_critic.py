@@ -75,6 +75,7 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
             replay_buffer=replay_buffer, update_func=self.update, batchsize=minibatch_size,
             n_times_update=1, replay_start_size=replay_start_size,
             update_interval=update_interval, episodic_update=False)
+        self.replay_updater.agent = self
         self.max_grad_norm = max_grad_norm
         self.batch_states = batch_states
         self.burnin_action_func = burnin_action_func
@@ -160,12 +161,22 @@ class SoftActorCritic(AttributeSavingMixin, BatchAgent):
             # sync per update in the reference, and illegal in graph capture)
             next_actions = next_distrib.rsample()
             next_log_prob = next_distrib.log_prob(next_actions)
-            next_q = torch.min(self.target_q_func1((next_state, next_actions)),
-                               self.target_q_func2((next_state, next_actions)))
-            entropy_term = self._temperature_tensor() * next_log_prob[..., None]
-            assert next_q.shape == entropy_term.shape
-            target_q = batch["reward"] + batch["discount"] * (
-                1.0 - batch["is_state_terminal"]) * torch.flatten(next_q - entropy_term)
+            next_q1 = self.target_q_func1((next_state, next_actions))
+            next_q2 = self.target_q_func2((next_state, next_actions))
+            assert next_q1.shape == next_log_prob[..., None].shape
+            if next_q1.is_cuda and next_q1.dtype == torch.float32:
+                # min, entropy term, (1 - terminal), discount and reward in one launch
+                # (b2rl_sac_target), rounded like the eager expression below
+                from pfrl_b200.ops.sac import sac_target
+
+                target_q = sac_target(batch["reward"], batch["discount"],
+                                      batch["is_state_terminal"], next_q1, next_q2,
+                                      next_log_prob, self._temperature_tensor())
+            else:
+                next_q = torch.min(next_q1, next_q2)
+                entropy_term = self._temperature_tensor() * next_log_prob[..., None]
+                target_q = batch["reward"] + batch["discount"] * (
+                    1.0 - batch["is_state_terminal"]) * torch.flatten(next_q - entropy_term)
         state, actions = batch["state"], batch["action"]
         predict_q1 = torch.flatten(self.q_func1((state, actions)))
         predict_q2 = torch.flatten(self.q_func2((state, actions)))

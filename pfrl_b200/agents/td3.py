@@ -128,6 +128,7 @@ class TD3(_OffPolicyActorCritic):
             replay_buffer=replay_buffer, update_func=self.update, batchsize=minibatch_size,
             n_times_update=1, replay_start_size=replay_start_size,
             update_interval=update_interval, episodic_update=False)
+        self.replay_updater.agent = self
         self.max_grad_norm = max_grad_norm
         self.policy_update_delay = policy_update_delay
         self.target_policy_smoothing_func = target_policy_smoothing_func
@@ -224,6 +225,7 @@ class DDPG(_OffPolicyActorCritic):
             episodic_update=False, episodic_update_len=episodic_update_len,
             n_times_update=n_times_update, replay_start_size=replay_start_size,
             update_interval=update_interval)
+        self.replay_updater.agent = self
         self.target_model = copy.deepcopy(self.model)
         self.target_model.eval()
         self.q_record = _DeviceRing(1000)

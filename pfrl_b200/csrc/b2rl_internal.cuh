@@ -80,6 +80,8 @@ struct b2rl_replay {
     // fused replay step (step.cu): cross-CTA "draws ready" counter, launch sequence
     // number, ring of pinned slots for host-drawn uniforms, deferred write-back
     unsigned long long *ready_dev;
+    unsigned long long *times_dev; // [8 + 256] %globaltimer stamps of the last fused launch
+    int last_step_grid;
     uint64_t step_seq;
     double *u_ring_pin, *u_ring_dev;
     cudaEvent_t u_ev[B2RL_U_RING];
@@ -115,8 +117,18 @@ int b2rl_stage_release(b2rl_replay *h, cudaStream_t s);
 static constexpr unsigned B2RL_N_TICKETS = 256;
 unsigned b2rl_next_ticket();
 
+// exact sampler generation for a tree of this depth (sampler.cu; env B2RL_SAMPLER=v5)
+bool b2rl_use_v6(int levels);
+int b2rl_v6_slow_every();
+double b2rl_v6_eps_scale();
+
 // Apply a write-back registered with b2rl_per_defer_errors (no-op if none).
 int b2rl_flush_pending(b2rl_replay *h, cudaStream_t s);
+
+// Ancestors of up to 4 ring-slot ranges (<= 512 leaves in total) recomputed by the
+// multi-CTA path kernel, then napp += bump_n and eviction down to capacity.
+int b2rl_launch_repair_multi(b2rl_replay *h, int nranges, const long long *first_slot,
+                             const long long *count, long long bump_n, cudaStream_t s);
 
 // Kernel launchers implemented in the other TUs.
 // Recompute the ancestors of up to 4 contiguous leaf-node ranges [lo, hi]

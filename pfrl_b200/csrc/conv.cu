@@ -32,14 +32,23 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p)
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// U8 = true: the images are uint8 (the replay gather's RAW output, 28 KB instead of
+// 113 KB per image); they are brought in by bulk async copies, double-buffered so that the
+// next image lands while this one is convolved, and expanded to float(x) * scale in
+// shared memory -- the very values the ScaleU8 gather would have written to HBM, so the
+// result is bit-identical to the f32 path.
+template <bool U8>
 __global__ void __launch_bounds__(THREADS, 1)
-k_conv_nature1(const float *__restrict__ x, const float *__restrict__ w,
+k_conv_nature1(const void *__restrict__ xin, float scale, const float *__restrict__ w,
                const float *__restrict__ bias, float *__restrict__ out, int n_images)
 {
     extern __shared__ __align__(128) float smem[];
     float *img = smem;              // [C][H][W]
     float *wsm = smem + IMG;        // [C][KS][KS][O]  (output channel fastest)
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + WSZ);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wsm + WSZ); // [2]
+    uint8_t *raw = reinterpret_cast<uint8_t *>(bar + 2);      // U8: [2][IMG] bytes
+    const float *x = static_cast<const float *>(xin);
+    const uint8_t *x8 = static_cast<const uint8_t *>(xin);
     const int tid = threadIdx.x;
 
     // filters: global [O][C][KS][KS] -> shared [C][KS][KS][O]
@@ -49,9 +58,22 @@ k_conv_nature1(const float *__restrict__ x, const float *__restrict__ w,
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar + 1)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    auto fetch_u8 = [&](int n, int buf) { // thread 0: image n -> raw[buf]
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                         smem_addr(bar + buf)),
+                     "r"(IMG)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                "r"(smem_addr(raw + (size_t)buf * IMG)),
+            "l"(x8 + (size_t)n * IMG), "r"(IMG), "r"(smem_addr(bar + buf))
+            : "memory");
+    };
+    if (U8 && tid == 0 && (int)blockIdx.x < n_images) fetch_u8(blockIdx.x, 0);
 
     const int cg = tid & 7;        // channels 4*cg .. 4*cg+3
     const int pg = tid >> 3;       // 0..39: output row = pg / 2, column half = pg & 1
@@ -61,26 +83,54 @@ k_conv_nature1(const float *__restrict__ x, const float *__restrict__ w,
 #pragma unroll
     for (int j = 0; j < 4; j++) b4[j] = bias ? bias[4 * cg + j] : 0.f;
 
-    uint32_t phase = 0;
-    for (int n = blockIdx.x; n < n_images; n += gridDim.x) {
-        if (tid == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
-                             smem_addr(bar)),
-                         "r"(IMG * 4)
-                         : "memory");
+    uint32_t phase = 0;       // f32 path: phase of bar[0]
+    uint32_t ph8[2] = {0, 0}; // u8 path: phases of bar[0], bar[1]
+    int it = 0;
+    for (int n = blockIdx.x; n < n_images; n += gridDim.x, it++) {
+        if constexpr (U8) {
+            const int buf = it & 1;
             asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                    "r"(smem_addr(img)),
-                "l"(x + (size_t)n * IMG), "r"(IMG * 4), "r"(smem_addr(bar))
+                "{\n.reg .pred p;\nW_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(smem_addr(bar + buf)),
+                "r"(ph8[buf])
                 : "memory");
+            ph8[buf] ^= 1;
+            // expand: 4 pixels per step, float(u8) * scale (= the ScaleU8 gather's arithmetic)
+            const uint32_t *r4 = reinterpret_cast<const uint32_t *>(raw + (size_t)buf * IMG);
+            float4 *i4 = reinterpret_cast<float4 *>(img);
+            for (int i = tid; i < IMG / 4; i += THREADS) {
+                const uint32_t v = r4[i];
+                float4 f;
+                f.x = (float)(v & 0xffu) * scale;
+                f.y = (float)((v >> 8) & 0xffu) * scale;
+                f.z = (float)((v >> 16) & 0xffu) * scale;
+                f.w = (float)(v >> 24) * scale;
+                i4[i] = f;
+            }
+            __syncthreads();
+            // the other byte buffer was expanded one iteration ago: refill it now
+            if (tid == 0 && n + (int)gridDim.x < n_images) fetch_u8(n + gridDim.x, buf ^ 1);
+        } else {
+            if (tid == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                                 smem_addr(bar)),
+                             "r"(IMG * 4)
+                             : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                        "r"(smem_addr(img)),
+                    "l"(x + (size_t)n * IMG), "r"(IMG * 4), "r"(smem_addr(bar))
+                    : "memory");
+            }
+            asm volatile(
+                "{\n.reg .pred p;\nW_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(smem_addr(bar)),
+                "r"(phase)
+                : "memory");
+            phase ^= 1;
         }
-        asm volatile(
-            "{\n.reg .pred p;\nW_%=:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-            "@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(smem_addr(bar)),
-            "r"(phase)
-            : "memory");
-        phase ^= 1;
 
         float acc[COLS][4];
 #pragma unroll
@@ -133,6 +183,31 @@ k_conv_nature1(const float *__restrict__ x, const float *__restrict__ w,
 
 } // namespace
 
+template <bool U8>
+static int launch_conv1(const void *x, float scale, const float *w, const float *bias,
+                        int32_t n_images, float *out, void *stream)
+{
+    const size_t smem = sizeof(float) * (IMG + WSZ) + 16 + (U8 ? 2 * (size_t)IMG : 0);
+    static bool attr_set[64]; // per device
+    int cur_dev = 0;
+    B2RL_CUDA(cudaGetDevice(&cur_dev));
+    if (cur_dev < 0 || cur_dev >= 64 || !attr_set[cur_dev]) {
+        B2RL_CUDA(cudaFuncSetAttribute(k_conv_nature1<U8>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (cur_dev >= 0 && cur_dev < 64) attr_set[cur_dev] = true;
+    }
+    static int sm_count = 0;
+    if (!sm_count) {
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cur_dev);
+        if (sm_count <= 0) sm_count = 148;
+    }
+    const int grid = n_images < sm_count ? n_images : sm_count;
+    k_conv_nature1<U8><<<grid, THREADS, smem, (cudaStream_t)stream>>>(x, scale, w, bias, out,
+                                                                     n_images);
+    B2RL_CUDA(cudaGetLastError());
+    return B2RL_OK;
+}
+
 extern "C" int b2rl_conv_nature1_fwd(const float *x, const float *w, const float *bias,
                                      int32_t n_images, float *out, void *stream)
 {
@@ -140,24 +215,16 @@ extern "C" int b2rl_conv_nature1_fwd(const float *x, const float *w, const float
     B2RL_REQUIRE(n_images > 0, B2RL_ERR_RANGE, "conv_nature1_fwd: empty batch");
     B2RL_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 7) == 0, B2RL_ERR_INVALID,
                  "conv_nature1_fwd: x must be 16-byte aligned, out 8-byte aligned");
-    const size_t smem = sizeof(float) * (IMG + WSZ) + 16;
-    static bool attr_set[64]; // per device
-    int cur_dev = 0;
-    B2RL_CUDA(cudaGetDevice(&cur_dev));
-    if (cur_dev < 0 || cur_dev >= 64 || !attr_set[cur_dev]) {
-        B2RL_CUDA(cudaFuncSetAttribute(k_conv_nature1, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        if (cur_dev >= 0 && cur_dev < 64) attr_set[cur_dev] = true;
-    }
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (sm_count <= 0) sm_count = 148;
-    }
-    const int grid = n_images < sm_count ? n_images : sm_count;
-    k_conv_nature1<<<grid, THREADS, smem, (cudaStream_t)stream>>>(x, w, bias, out, n_images);
-    B2RL_CUDA(cudaGetLastError());
-    return B2RL_OK;
+    return launch_conv1<false>(x, 1.0f, w, bias, n_images, out, stream);
+}
+
+extern "C" int b2rl_conv_nature1_fwd_u8(const uint8_t *x, float scale, const float *w,
+                                        const float *bias, int32_t n_images, float *out,
+                                        void *stream)
+{
+    B2RL_REQUIRE(x && w && out, B2RL_ERR_INVALID, "conv_nature1_fwd_u8: null argument");
+    B2RL_REQUIRE(n_images > 0, B2RL_ERR_RANGE, "conv_nature1_fwd_u8: empty batch");
+    B2RL_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 7) == 0, B2RL_ERR_INVALID,
+                 "conv_nature1_fwd_u8: x must be 16-byte aligned, out 8-byte aligned");
+    return launch_conv1<true>(x, scale, w, bias, n_images, out, stream);
 }

@@ -15,6 +15,7 @@
 // ancestors level by level.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <atomic>
@@ -279,6 +280,12 @@ static int create_impl(b2rl_replay *h)
         k_fill_f64<<<1024, 256>>>(h->mn, 2 * h->nslots, INFINITY);
         k_fill_i32<<<1024, 256>>>(h->winner, h->nslots, -1);
     }
+    // [0] draws-ready counter of the fused step, [1] write-back-done stamp, [2] arrival counter
+    B2RL_CUDA(cudaMalloc((void **)&h->ready_dev, 128));
+    B2RL_CUDA(cudaMemset(h->ready_dev, 0, 128));
+    B2RL_CUDA(cudaMalloc((void **)&h->times_dev, 8 * (8 + 256)));
+    B2RL_CUDA(cudaMemset(h->times_dev, 0, 8 * (8 + 256)));
+    h->device_bytes += 128 + 8 * (8 + 256);
     B2RL_CUDA(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
     B2RL_CUDA(cudaGetLastError());
     B2RL_CUDA(cudaDeviceSynchronize());
@@ -334,6 +341,7 @@ extern "C" int b2rl_replay_destroy(b2rl_replay *h)
     if (h->pin) cudaFreeHost(h->pin);
     if (h->stage_ev) cudaEventDestroy(h->stage_ev);
     if (h->ready_dev) cudaFree(h->ready_dev);
+    if (h->times_dev) cudaFree(h->times_dev);
     if (h->u_ring_dev) cudaFree(h->u_ring_dev);
     if (h->u_ring_pin) cudaFreeHost(h->u_ring_pin);
     for (int i = 0; i < B2RL_U_RING; i++)
@@ -388,6 +396,23 @@ extern "C" int b2rl_replay_put_parts(b2rl_replay *h, const void *src, int src_on
 int b2rl_launch_tree_fix(b2rl_replay *h, int nranges, long long *lo, long long *hi,
                          long long bump_n, cudaStream_t s)
 {
+    if (h->cfg.prioritized && nranges > 0) {
+        // small appends (one vector-env step): path-wise repair on up to 128 SMs instead
+        // of a level-synchronous walk on one (42 us -> a few us)
+        long long total = 0, first[4], cnt[4];
+        for (int r = 0; r < nranges; r++) {
+            first[r] = lo[r] - h->nslots;
+            cnt[r] = hi[r] - lo[r] + 1;
+            total += cnt[r];
+        }
+        static int level_sync = -1; // B2RL_REPAIR=levels keeps the old kernels
+        if (level_sync < 0) {
+            const char *e = getenv("B2RL_REPAIR");
+            level_sync = (e && e[0] == 'l') ? 1 : 0;
+        }
+        if (total <= 512 && !level_sync)
+            return b2rl_launch_repair_multi(h, nranges, first, cnt, bump_n, s);
+    }
     int level = h->levels; // lo/hi are leaf-level node indices
     if (h->cfg.prioritized) {
         // wide phase: one multi-CTA launch per level and range

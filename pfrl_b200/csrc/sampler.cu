@@ -91,8 +91,72 @@ static cudaError_t launch_deep(const SampleArgs &a, cudaStream_t s)
                                    : launch_deep_as<D, false>(a, s);
 }
 
+// v6 (tree_dev.cuh): decisions on an approximate top, exact re-reduction on a trailing warp
+template <int D>
+__global__ void __launch_bounds__(V6_THREADS, 1) k_sample_exact_v6(SampleArgs a)
+{
+    exact_deep_v6<D, true>(a, reinterpret_cast<double *>(smem_raw));
+}
+
+template <int D>
+static cudaError_t launch_v6_as(const SampleArgs &a, cudaStream_t s)
+{
+    const size_t smem = exact_v6_smem_bytes<D>();
+    static bool done[64];
+    cudaError_t e = allow_smem(k_sample_exact_v6<D>, smem, done);
+    if (e != cudaSuccess) return e;
+    k_sample_exact_v6<D><<<1, V6_THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// B2RL_SAMPLER=v5 keeps the single-chain sampler for trees v6 covers (levels 17..21)
+bool b2rl_use_v6(int levels)
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("B2RL_SAMPLER");
+        cached = (e && e[0] == 'v' && e[1] == '5') ? 0 : 1;
+    }
+    return cached == 1 && levels >= 17 && levels <= 21; // v6 stages 5..9 levels per draw
+}
+
+int b2rl_v6_slow_every()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("B2RL_V6_SLOW_EVERY");
+        cached = e ? atoi(e) : 0;
+        if (cached < 0) cached = 0;
+    }
+    return cached;
+}
+
+double b2rl_v6_eps_scale()
+{
+    static double cached = -1.0;
+    if (cached < 0.0) {
+        const char *e = getenv("B2RL_V6_EPS_SCALE");
+        cached = e ? atof(e) : 0.0;
+        if (cached < 0.0) cached = 0.0;
+    }
+    return cached;
+}
+
+static cudaError_t launch_exact_v6(const SampleArgs &a, cudaStream_t s)
+{
+    switch (a.levels - (V6_T - 1)) {
+    case 5: return launch_v6_as<5>(a, s);
+    case 6: return launch_v6_as<6>(a, s);
+    case 7: return launch_v6_as<7>(a, s);
+    case 8: return launch_v6_as<8>(a, s);
+    case 9: return launch_v6_as<9>(a, s);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 static cudaError_t launch_exact_deep(const SampleArgs &a, cudaStream_t s)
 {
+    if (b2rl_use_v6(a.levels)) return launch_exact_v6(a, s);
     switch (a.D) {
     case 1: return launch_deep<1>(a, s);
     case 2: return launch_deep<2>(a, s);
@@ -154,6 +218,8 @@ extern "C" int b2rl_per_sample(b2rl_replay *h, const double *u_host, int32_t n, 
     a.norm = B2RL_NORM_NONE;
     a.ready = nullptr;
     a.seq_base = 0;
+    a.dbg_slow_every = b2rl_v6_slow_every();
+    a.dbg_eps_scale = b2rl_v6_eps_scale();
     if (mode == B2RL_SAMPLE_EXACT && a.D > 0) {
         B2RL_CUDA(launch_exact_deep(a, s));
     } else if (mode == B2RL_SAMPLE_EXACT) {
@@ -242,6 +308,13 @@ extern "C" int b2rl_per_weights(b2rl_replay *h, double beta, int norm, float *we
 __global__ void __launch_bounds__(512, 1) k_update_paths(UpdateArgs a)
 {
     tree_update_paths(a, smem_raw);
+}
+
+// one CTA per subtree below level 7, the last one to arrive finishes the top
+__global__ void __launch_bounds__(256) k_update_multi(UpdateArgs a, unsigned long long *sync,
+                                                      unsigned long long seq)
+{
+    tree_update_multi(a, smem_raw, sync, seq);
 }
 
 __global__ void __launch_bounds__(1024) k_update(UpdateArgs a)
@@ -364,10 +437,25 @@ static int launch_update(b2rl_replay *h, int32_t n, const void *err, int err_is_
     a.n = n;
     a.levels = h->levels;
     a.nslots = h->nslots;
-    if (n <= UPD_MAX) {
+    a.nranges = 0;
+    a.bump_n = 0;
+    a.capacity = h->cfg.capacity;
+    static int single_cta = -1; // B2RL_UPDATE=single keeps the one-CTA sorted-path kernel
+    if (single_cta < 0) {
+        const char *e = getenv("B2RL_UPDATE");
+        single_cta = (e && e[0] == 's') ? 1 : 0;
+    }
+    if (n <= UPD_MAX && !single_cta) {
+        const size_t smem = update_multi_smem_bytes(h->levels);
+        static bool done[64];
+        B2RL_CUDA(allow_smem(k_update_multi, 227 * 1024, done)); // once per device: the maximum
+        const int grid = 1 << update_split_level(h->levels);
+        k_update_multi<<<grid, 256, smem, s>>>(a, h->ready_dev + 1,
+                                               (unsigned long long)h->step_seq << 32);
+    } else if (n <= UPD_MAX) {
         const size_t smem = update_paths_smem_bytes(h->levels);
         static bool done[64];
-        B2RL_CUDA(allow_smem(k_update_paths, 227 * 1024, done)); // once per device: the maximum
+        B2RL_CUDA(allow_smem(k_update_paths, 227 * 1024, done));
         k_update_paths<<<1, 512, smem, s>>>(a);
     } else {
         k_update<<<1, 1024, 0, s>>>(a);
@@ -420,6 +508,37 @@ extern "C" int b2rl_per_update_errors(b2rl_replay *h, const void *err_dev, int e
     B2RL_CUDA(cudaSetDevice(h->cfg.device));
     return launch_update(h, n, err_dev, err_is_f64, alpha, eps, error_min, error_max,
                          (cudaStream_t)stream);
+}
+
+// Ancestor repair after a small append: same multi-CTA kernel, "repair" mode.
+int b2rl_launch_repair_multi(b2rl_replay *h, int nranges, const long long *first_slot,
+                             const long long *count, long long bump_n, cudaStream_t s)
+{
+    UpdateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sum = h->sum;
+    a.mn = h->mn;
+    a.st = h->st;
+    a.levels = h->levels;
+    a.nslots = h->nslots;
+    a.nranges = nranges;
+    int total = 0;
+    for (int r = 0; r < nranges; r++) {
+        a.r_first[r] = (int)first_slot[r];
+        a.r_count[r] = (int)count[r];
+        total += (int)count[r];
+    }
+    a.n = total;
+    a.bump_n = bump_n;
+    a.capacity = h->cfg.capacity;
+    const size_t smem = update_multi_smem_bytes(h->levels);
+    static bool done[64];
+    B2RL_CUDA(allow_smem(k_update_multi, 227 * 1024, done));
+    const int grid = 1 << update_split_level(h->levels);
+    k_update_multi<<<grid, 256, smem, s>>>(a, h->ready_dev + 1,
+                                           (unsigned long long)h->step_seq << 32);
+    B2RL_CUDA(cudaGetLastError());
+    return B2RL_OK;
 }
 
 // Deferred form: register the TD errors of the last sample; the trees are

@@ -63,8 +63,19 @@ struct StepArgs {
     SampleArgs s;
     UpdateArgs u;
     int upd_n; // > 0: write back the previous sample first
+    unsigned long long *upd_sync; // [0] done stamp, [1] arrival counter
+    // %globaltimer stamps of this launch (b2rl_step_times): [0] CTA 0 entry, [1] write-back
+    // complete, [2] all draws published, [8 + c] exit of CTA c
+    unsigned long long *times;
     StepGather g;
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 extern __shared__ __align__(128) unsigned char smem_raw[];
 
@@ -248,21 +259,38 @@ __device__ __forceinline__ void gather_worker(const StepGather &g, unsigned char
     }
 }
 
-// MODE 0: exact, deep tree (template D); 1: exact, tree in shared memory; 2: parallel
+// MODE 0: exact v5, deep tree (template D = levels - 13); 1: exact, tree in shared memory;
+// 2: parallel; 3: exact v6 (template D = levels - 12)
 template <int D, int MODE>
 __global__ void __launch_bounds__(STEP_THREADS, 1) k_replay_step(const __grid_constant__ StepArgs a)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.times[0] = global_ns();
+    if (a.upd_n > 0) {
+        // write-back of the previous sample: every CTA takes the subtrees it owns; the
+        // sampler (CTA 0) waits for the one that finishes the top of the tree
+        tree_update_multi(a.u, smem_raw, a.upd_sync, a.s.seq_base);
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0)
+                while (ld_acquire_gpu(a.upd_sync) != a.s.seq_base) __nanosleep(100);
+            __syncthreads();
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.times[1] = global_ns();
     if (blockIdx.x == 0) {
-        if (a.upd_n > 0) tree_update_paths(a.u, smem_raw);
         if constexpr (MODE == 0)
             exact_deep<D, true>(a.s, reinterpret_cast<double *>(smem_raw));
+        else if constexpr (MODE == 3)
+            exact_deep_v6<D, true>(a.s, reinterpret_cast<double *>(smem_raw));
         else if constexpr (MODE == 1)
             exact_small(a.s, reinterpret_cast<double *>(smem_raw));
         else
             sample_parallel(a.s, reinterpret_cast<double *>(smem_raw));
+        if (threadIdx.x == 0) a.times[2] = global_ns();
     } else {
         gather_worker(a.g, smem_raw, blockIdx.x - 1, gridDim.x - 1);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) a.times[8 + blockIdx.x] = global_ns();
 }
 
 template <int D, int MODE>
@@ -297,6 +325,16 @@ static cudaError_t launch_step(const StepArgs &a, int mode, int grid, size_t sme
         const size_t sm = sizeof(double) * ((size_t(1) << a.s.T) + 2);
         return launch_step_as<0, 1>(a, grid, mx(smem_other, sm), s);
     }
+    if (b2rl_use_v6(a.s.levels)) {
+        switch (a.s.levels - (V6_T - 1)) {
+        case 5: return launch_step_as<5, 3>(a, grid, mx(smem_other, exact_v6_smem_bytes<5>()), s);
+        case 6: return launch_step_as<6, 3>(a, grid, mx(smem_other, exact_v6_smem_bytes<6>()), s);
+        case 7: return launch_step_as<7, 3>(a, grid, mx(smem_other, exact_v6_smem_bytes<7>()), s);
+        case 8: return launch_step_as<8, 3>(a, grid, mx(smem_other, exact_v6_smem_bytes<8>()), s);
+        case 9: return launch_step_as<9, 3>(a, grid, mx(smem_other, exact_v6_smem_bytes<9>()), s);
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (a.s.D) {
     case 1: return launch_step_as<1, 0>(a, grid, mx(smem_other, deep_bytes<1>()), s);
     case 2: return launch_step_as<2, 0>(a, grid, mx(smem_other, deep_bytes<2>()), s);
@@ -317,9 +355,7 @@ static cudaError_t launch_step(const StepArgs &a, int mode, int grid, size_t sme
 // ---------------------------------------------------------------------------
 static int step_resources(b2rl_replay *h)
 {
-    if (h->ready_dev) return B2RL_OK;
-    B2RL_CUDA(cudaMalloc((void **)&h->ready_dev, 128));
-    B2RL_CUDA(cudaMemset(h->ready_dev, 0, 128));
+    if (h->u_ring_dev) return B2RL_OK;
     const size_t ring = (size_t)B2RL_U_RING * h->cfg.max_batch * sizeof(double);
     B2RL_CUDA(cudaMallocHost((void **)&h->u_ring_pin, ring));
     B2RL_CUDA(cudaMalloc((void **)&h->u_ring_dev, ring));
@@ -328,7 +364,7 @@ static int step_resources(b2rl_replay *h)
     int sm = 0;
     B2RL_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, h->cfg.device));
     h->sm_count = sm;
-    h->device_bytes += 128 + (int64_t)ring;
+    h->device_bytes += (int64_t)ring;
     return B2RL_OK;
 }
 
@@ -401,6 +437,8 @@ extern "C" int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *p, void *s
     a.s.norm = p->norm;
     a.s.ready = h->ready_dev;
     a.s.seq_base = seq_base;
+    a.s.dbg_slow_every = b2rl_v6_slow_every();
+    a.s.dbg_eps_scale = b2rl_v6_eps_scale();
     // ---- deferred write-back of the previous sample
     a.upd_n = 0;
     if (h->pending) {
@@ -420,7 +458,9 @@ extern "C" int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *p, void *s
         a.u.levels = h->levels;
         a.u.nslots = h->nslots;
         a.upd_n = h->pend_n;
+        a.upd_sync = h->ready_dev + 1;
     }
+    a.times = h->times_dev;
     // ---- gather
     StepGather &g = a.g;
     g.parts = h->parts;
@@ -461,13 +501,39 @@ extern "C" int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *p, void *s
     if (grid < 2) grid = 2;
     size_t smem = (size_t)GS * g.stage_stride + 2 * GS * sizeof(uint64_t);
     if (a.upd_n > 0) {
-        const size_t us = update_paths_smem_bytes(h->levels);
+        const size_t us = update_multi_smem_bytes(h->levels);
         if (us > smem) smem = us;
     }
+    h->last_step_grid = grid;
     B2RL_CUDA(launch_step(a, p->mode, grid, smem, s));
     h->pending = false;
     h->wait_priority = true;
     h->last_n = n;
     h->last_mode = p->mode;
+    return B2RL_OK;
+}
+
+// Phase durations of the LAST fused step launch, from %globaltimer stamps the kernel
+// leaves behind (synchronises the stream): out_ns[0] write-back, [1] sampling (first
+// draw to last draw published), [2] gather tail (last draw published -> last CTA exits),
+// [3] whole launch (CTA 0 entry -> last CTA exits).
+extern "C" int b2rl_step_times(b2rl_replay *h, uint64_t *out_ns, void *stream)
+{
+    B2RL_REQUIRE(h && out_ns, B2RL_ERR_INVALID, "null argument");
+    B2RL_REQUIRE(h->last_step_grid > 0, B2RL_ERR_PROTOCOL, "no fused step was launched yet");
+    cudaStream_t s = (cudaStream_t)stream;
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    unsigned long long t[8 + 256];
+    const int grid = h->last_step_grid < 248 ? h->last_step_grid : 248;
+    B2RL_CUDA(cudaMemcpyAsync(t, h->times_dev, sizeof(unsigned long long) * (8 + grid),
+                              cudaMemcpyDeviceToHost, s));
+    B2RL_CUDA(cudaStreamSynchronize(s));
+    unsigned long long last = 0;
+    for (int c = 0; c < grid; c++)
+        if (t[8 + c] > last) last = t[8 + c];
+    out_ns[0] = t[1] - t[0];
+    out_ns[1] = t[2] - t[1];
+    out_ns[2] = last > t[2] ? last - t[2] : 0;
+    out_ns[3] = last - t[0];
     return B2RL_OK;
 }

@@ -43,6 +43,10 @@ struct SampleArgs {
     // *ready = seq_base | (number of draws whose outputs are visible)
     unsigned long long *ready;
     unsigned long long seq_base;
+    // v6 test hooks (env B2RL_V6_SLOW_EVERY / B2RL_V6_EPS_SCALE): force the exact slow
+    // path on every k-th draw / widen the decision margin; results must not change
+    int dbg_slow_every;
+    double dbg_eps_scale;
 };
 
 // ---------------------------------------------------------------------------
@@ -730,6 +734,12 @@ struct UpdateArgs {
     int32_t *winner;        // scratch of the level-synchronous kernel (n > UPD_MAX)
     int n, levels;
     long long nslots;
+    // "repair" mode (append / eviction): the n touched leaves are the ring-slot ranges
+    // below and already hold their values; only their ancestors are recomputed, then the
+    // append / pop counters advance (collections/prioritized.py:207-242)
+    int nranges;            // 0: normal write-back
+    int r_first[4], r_count[4];
+    long long bump_n, capacity;
 };
 
 __host__ __device__ inline size_t update_paths_smem_bytes(int levels)
@@ -878,4 +888,697 @@ __device__ __forceinline__ void tree_update_paths(const UpdateArgs &a, unsigned 
         a.st->last_n = 0;
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// Multi-CTA write-back.  tree_update_paths above is bound by ONE SM's L1TEX: the
+// ~21 x 512 x 2 scattered 8-byte sibling loads are ~20 k wavefronts, ~2 cycles
+// each (42 us measured).  The heap splits into 2^sl independent subtrees below
+// level sl (sl = min(7, levels)): CTA c runs the sorted-path algorithm on the
+// updated leaves that fall into subtree c (typically 4 of 512) -- all subtrees
+// in parallel on different SMs -- and the LAST CTA to arrive (atomic ticket)
+// recomputes the 2^sl - 1 nodes above from the subtree roots (every node is a
+// pure function of its children, so recomputing untouched ones changes
+// nothing).  sync[0] = "write-back of launch `seq` complete" (release/acquire),
+// sync[1] = arrival counter (self-resetting atomicInc).
+// Called by all threads of every CTA of the grid; n <= UPD_MAX.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int update_split_level(int levels) { return levels < 7 ? levels : 7; }
+
+__host__ __device__ inline size_t update_multi_smem_bytes(int levels)
+{
+    const int lb = levels - update_split_level(levels);
+    return (size_t)UPD_MAX * (5 * 4 + 3 * 8) + 64 * 8 + (size_t)lb * UPD_MAX * 16 + 2 * 256 * 8;
+}
+
+__device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned char *smem_raw,
+                                                  unsigned long long *sync,
+                                                  unsigned long long seq)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int sl = update_split_level(a.levels);
+    const int lb = a.levels - sl;           // levels inside one subtree
+    const int NS = 1 << sl;
+    double *prio_k = reinterpret_cast<double *>(smem_raw);     // [UPD_MAX] by draw index
+    double *vs = prio_k + UPD_MAX;                             // [UPD_MAX] by sorted entry
+    double *vm = vs + UPD_MAX;
+    double *red = vm + UPD_MAX;                                // [64]
+    double *sib_s = red + 64;                                  // [lb][UPD_MAX]
+    double *sib_m = sib_s + (size_t)lb * UPD_MAX;
+    double *t_sum = sib_m + (size_t)lb * UPD_MAX;              // [256] top phase
+    double *t_min = t_sum + 256;
+    unsigned *keys = reinterpret_cast<unsigned *>(t_min + 256); // [UPD_MAX] unsorted
+    unsigned *skeys = keys + UPD_MAX;                          // [UPD_MAX] sorted
+    int *leaf = reinterpret_cast<int *>(skeys + UPD_MAX);      // [UPD_MAX] slot inside the ring
+    int *runlen = leaf + UPD_MAX;
+    int *lead = runlen + UPD_MAX;
+    int *ctr = reinterpret_cast<int *>(red) + 64;              // [0] count, [1] last flag, [2..] group counts
+    double mx = 0.0;
+
+    for (int st = blockIdx.x; st < NS; st += gridDim.x) {
+        if (tid == 0) ctr[0] = 0;
+        __syncthreads();
+        // ---- collect the draws whose leaf lies in subtree `st`
+        for (int k = tid; k < a.n; k += nt) {
+            int slot;
+            if (a.nranges > 0) {
+                int r = 0, off = k;
+                while (off >= a.r_count[r]) off -= a.r_count[r++];
+                slot = a.r_first[r] + off;
+            } else {
+                slot = a.slots[k];
+            }
+            if ((slot >> lb) != st) continue;
+            if (a.nranges == 0) {
+                const double p = a.err ? priority_from_error(a, k) : a.new_prio[k];
+                if (a.err) a.new_prio[k] = p;
+                prio_k[k] = p;
+                mx = fmax(mx, p); // max_priority sees every value, :114
+            }
+            const int pos = atomicAdd(&ctr[0], 1);
+            keys[pos] = ((unsigned)(slot & ((1 << lb) - 1)) << 16) | (unsigned)k;
+        }
+        __syncthreads();
+        const int cnt = ctr[0];
+        if (cnt == 0) continue; // uniform
+        // ---- rank sort by (slot, draw index); keys are distinct
+        for (int i = tid; i < cnt; i += nt) {
+            const unsigned key = keys[i];
+            int rank = 0;
+            for (int j = 0; j < cnt; j++) rank += keys[j] < key;
+            skeys[rank] = key;
+        }
+        __syncthreads();
+        // ---- unique leaves (last occurrence of a slot wins), compaction
+        const int ngroups = (cnt + 31) >> 5;
+        for (int g = warp; g < ngroups; g += nw) {
+            const int i = g * 32 + lane;
+            const bool w = i < cnt && (i == cnt - 1 || (skeys[i + 1] >> 16) != (skeys[i] >> 16));
+            const unsigned b = __ballot_sync(0xffffffffu, w);
+            if (lane == 0) ctr[2 + g] = __popc(b);
+        }
+        __syncthreads();
+        int m = 0;
+        for (int g = 0; g < ngroups; g++) m += ctr[2 + g];
+        for (int g = warp; g < ngroups; g += nw) {
+            const int i = g * 32 + lane;
+            const bool w = i < cnt && (i == cnt - 1 || (skeys[i + 1] >> 16) != (skeys[i] >> 16));
+            const unsigned b = __ballot_sync(0xffffffffu, w);
+            int base = 0;
+            for (int q = 0; q < g; q++) base += ctr[2 + q];
+            if (w) {
+                const int pos = base + __popc(b & ((1u << lane) - 1u));
+                const int lf = (st << lb) | (int)(skeys[i] >> 16);
+                leaf[pos] = lf;
+                if (a.nranges > 0) { // repair: the leaves are already in place
+                    vs[pos] = a.sum[a.nslots + lf];
+                    vm[pos] = a.mn[a.nslots + lf];
+                } else {
+                    const double p = prio_k[skeys[i] & 0xffffu];
+                    vs[pos] = p;
+                    vm[pos] = p;
+                }
+                runlen[pos] = 1;
+                lead[pos] = 1;
+            }
+        }
+        __syncthreads();
+        // ---- leaves out, every sibling of every path inside the subtree in
+        if (a.nranges == 0)
+            for (int i = tid; i < m; i += nt) {
+                const long long ln = a.nslots + leaf[i];
+                a.sum[ln] = vs[i];
+                a.mn[ln] = vm[i];
+            }
+        for (int idx = tid; idx < m * lb; idx += nt) {
+            const int i = idx % m, s = idx / m;
+            const long long node = (a.nslots + leaf[i]) >> s;
+            sib_s[(size_t)s * UPD_MAX + i] = a.sum[node ^ 1];
+            sib_m[(size_t)s * UPD_MAX + i] = a.mn[node ^ 1];
+        }
+        __syncthreads();
+        // ---- level loop on shared memory (see tree_update_paths)
+        for (int s = 0; s < lb; s++) {
+            for (int i = tid; i < m; i += nt) {
+                if (!lead[i]) continue;
+                const long long node = (a.nslots + leaf[i]) >> s;
+                double ns, nm;
+                if ((node & 1) == 0) {
+                    const int j = i + runlen[i];
+                    if (j < m && ((a.nslots + leaf[j]) >> s) == node + 1) {
+                        ns = __dadd_rn(vs[i], vs[j]);
+                        nm = fmin(vm[i], vm[j]);
+                        runlen[i] += runlen[j];
+                    } else {
+                        ns = __dadd_rn(vs[i], sib_s[(size_t)s * UPD_MAX + i]);
+                        nm = fmin(vm[i], sib_m[(size_t)s * UPD_MAX + i]);
+                    }
+                } else {
+                    if (i > 0 && ((a.nslots + leaf[i - 1]) >> s) == node - 1) {
+                        lead[i] = 0;
+                        continue;
+                    }
+                    ns = __dadd_rn(sib_s[(size_t)s * UPD_MAX + i], vs[i]);
+                    nm = fmin(sib_m[(size_t)s * UPD_MAX + i], vm[i]);
+                }
+                vs[i] = ns;
+                vm[i] = nm;
+                a.sum[node >> 1] = ns;
+                a.mn[node >> 1] = nm;
+            }
+            __syncthreads();
+        }
+    }
+    // ---- max_priority (positive doubles order like their bit patterns), arrival
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __threadfence(); // this thread's node stores before the CTA's arrival ticket
+    __syncthreads();
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nw; w++) mx = fmax(mx, red[w]);
+        if (mx > 0.0)
+            atomicMax(reinterpret_cast<unsigned long long *>(&a.st->max_priority),
+                      (unsigned long long)__double_as_longlong(mx));
+        __threadfence();
+        const unsigned prev = atomicInc(reinterpret_cast<unsigned *>(sync + 1), gridDim.x - 1);
+        ctr[1] = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (ctr[1]) {
+        // ---- last CTA: the sl levels above the subtree roots
+        __threadfence();
+        for (int i = tid; i < NS; i += nt) {
+            t_sum[NS + i] = __ldcg(a.sum + NS + i);
+            t_min[NS + i] = __ldcg(a.mn + NS + i);
+        }
+        __syncthreads();
+        for (int lv = sl - 1; lv >= 0; lv--) {
+            const int w = 1 << lv;
+            for (int i = tid; i < w; i += nt) {
+                const int node = w + i;
+                t_sum[node] = __dadd_rn(t_sum[2 * node], t_sum[2 * node + 1]);
+                t_min[node] = fmin(t_min[2 * node], t_min[2 * node + 1]);
+            }
+            __syncthreads();
+        }
+        for (int i = 1 + tid; i < NS; i += nt) {
+            a.sum[i] = t_sum[i];
+            a.mn[i] = t_min[i];
+        }
+        if (tid == 0) {
+            if (a.nranges == 0) {
+                a.st->last_n = 0;
+            } else if (a.bump_n > 0) {
+                long long napp = a.st->napp + a.bump_n;
+                long long npop = a.st->npop;
+                if (napp - npop > a.capacity) npop = napp - a.capacity;
+                a.st->napp = napp;
+                a.st->npop = npop;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release_gpu(sync, seq);
+    }
+}
+
+// ===========================================================================
+// EXACT sampler v6: decisions on approximate prefix tables, proofs by margin,
+// the exact re-reduction trails on its own warp.
+//
+// The reference's draw k is a dependent chain: pos = u_k * root_k, 21 compare /
+// subtract steps down, then `_write(ix, 0.0)` re-reduces 21 nodes bottom-up
+// (each fl(left + right)) to give root_k+1 -- and only then can draw k+1 start
+// (collections/prioritized.py:245-258, 294-312, 140-180).  v5 walks exactly
+// that chain on one warp (~0.75 us per draw: ~400 dependent instructions).
+//
+// What the caller needs from draw k is only the LEAF (its index and priority);
+// `pos` is thrown away.  The leaf is determined by the signs of the comparisons
+// `pos_j < left_j`, and a sign can be proven without the exact operands: the
+// positions that lead to a given node form an interval [prefix, prefix + mass)
+// of the descent order, so if approximations of prefix and mass with error
+// < EPS put pos farther than EPS inside the interval, every comparison on the
+// way has the reference's outcome.  So:
+//
+//   * top 13 levels -> three approximate tables over the 4096 level-12 nodes in
+//     descent order (the reference visits the OLDER half of the ring first):
+//     M[o] mass, P_lo[o] prefix inside its block of 64, P_hi[b] prefix of the
+//     blocks.  After a draw of priority p at node o they are updated by plain
+//     subtractions, all entries at once (lanes): M[o], P_lo[e > o in the
+//     block], P_hi[b' > block].  Errors: each entry sees <= n roundings of
+//     <= 2^-53 root, the initial sums <= 80; EPS = (n + 64) 2^-46 root is > 40x
+//     everything a decision depends on (DESIGN.md has the budget).
+//   * bottom 9 levels -> the scout that stages the predicted node's subtree
+//     (exact values, one global round trip, ~4 draws ahead) also lays down the
+//     running sums Q[0..512] of its 512 leaves.
+//   * the main warp decides draw k with
+//         pos12 = u_k * rootA - P_hi[o >> 6] - P_lo[o]   (must be in (EPS, M[o] - EPS))
+//         two 32-way compares of pos12 against Q         (leaf i; pos12 farther
+//                                                         than EPS from Q[i], Q[i+1])
+//     and no draw still in flight in the exact pipeline touched that subtree.
+//     Any doubt (late or wrong scout, margin, conflict) -> SLOW PATH: wait until
+//     the exact tree has caught up and run the reference's arithmetic on it (the
+//     v5 code).  Never wrong, only slow; the count is reported
+//     (b2rl_per_info.scout_hits: fast | slow << 16).
+//   * the ascent warp applies draw k to the EXACT tree (shared-memory top +
+//     global bottom) with the reference's bottom-up adds, one draw after the
+//     other, a few draws behind.  The tree that goes back to HBM and every
+//     priority returned are exact.
+//   * four scout warps; a publisher warp moves results out.
+// tools/v6_model.py is a CPU model of the decision logic (adversarial trees:
+// ties, 1e-30..1e+30 dynamic range, u on boundaries, mispredictions).
+// ===========================================================================
+static constexpr int V6_T = 13;
+static constexpr int V6_NSCOUT = 4;
+static constexpr int V6_LAG = 4;
+static constexpr int V6_NBUF = 6;
+static constexpr int V6_HIST = 64;
+static constexpr int V6_Q = 16;
+static constexpr int V6_NTOP = 1 << (V6_T - 1);  // 4096 level-12 nodes
+// Warp roles.  The issue arbiter of an SM sub-partition (warp id % 4) prefers its
+// highest eligible warp id, so the latency-critical main warp gets a sub-partition to
+// itself and all four scouts share another one.
+static constexpr int V6_W_MAIN = 3, V6_W_ASC = 1, V6_W_PUB = 2; // scouts: warps 0, 4, 8, 12
+static constexpr int V6_THREADS = 512;
+
+// One staged subtree: [internal nodes, relative heap index < 2^D][LT: leaves, transposed]
+// [QT: running sums of the leaves, transposed][QB: 32 block starts + total].  Leaf e of
+// the 2^D leaves belongs to lane e / PER (PER = 2^D / 32) and sits at (e % PER) * 33 +
+// e / PER: the scouts' per-lane runs and the main warp's two 32-way look-ups are all
+// free of shared-memory bank conflicts (a plain [lane][i] layout costs 32-way conflicts).
+__host__ __device__ constexpr size_t v6_buf_doubles(int D)
+{
+    return (size_t(1) << D) + 2 * ((size_t(1) << D) / 32) * 33 + 40;
+}
+
+template <int D>
+__host__ __device__ constexpr size_t exact_v6_smem_bytes()
+{
+    // etop, M, P_lo, P_hi(64) + rootA + stat(2) + pad, sub_own, NBUF x staged buffer, o_prio
+    return sizeof(double) * ((size_t(1) << V6_T) + 2 * V6_NTOP + 72 + (size_t(2) << D) +
+                             V6_NBUF * v6_buf_doubles(D) + EX_RING) +
+           sizeof(int) * (EX_RING + V6_HIST + 3 * V6_Q + 32) + 16;
+}
+
+template <int D, bool FMA>
+__device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_d)
+{
+    constexpr int T = V6_T;
+    constexpr int TOPN = 1 << T;
+    constexpr int NTOP = V6_NTOP;
+    constexpr int SUBN = 2 << D;
+    constexpr int NLEAF = 1 << D;               // leaves under one level-12 node
+    constexpr int PER = NLEAF / 32;             // consecutive leaves owned by one lane
+    constexpr int TR = PER * 33;                // size of a transposed leaf array
+    constexpr int BUFN = (int)v6_buf_doubles(D);
+    constexpr int O_LT = NLEAF, O_QT = NLEAF + TR, O_QB = NLEAF + 2 * TR;
+    constexpr int PAIRS = (1 << D) - 1;         // child pairs of a whole subtree (slow path)
+    constexpr int NIT = (PAIRS + 31) / 32;
+    constexpr int IPAIRS = NLEAF / 2 - 1;       // child pairs above the leaf level
+    constexpr int INIT = (IPAIRS + 31) / 32;
+    constexpr int CHUNK = 32;
+    constexpr int NSCOUT = V6_NSCOUT, LAG = V6_LAG, NBUF = V6_NBUF, RING = EX_RING;
+    constexpr int HIST = V6_HIST, Q = V6_Q;
+    // F_ASC:  draws whose exact update is VISIBLE (global stores fenced), published in
+    //         batches -- the fence waits for the L2 acknowledgement of the ascent's global
+    //         stores and a MEMBAR holds up the SM's shared-memory pipe for everybody, so it
+    //         must not be paid per draw;
+    // F_ASCR: draws the ascent warp has finished READING the inputs of (relaxed, per draw):
+    //         staged buffers and queue slots can be reused.
+    constexpr int F_READY = 0, F_ORD = 8, F_SEEN = 16, F_MAIN = 24, F_ASC = 25, F_PUB = 26,
+                  F_ASCR = 27;
+    constexpr int ASC_BATCH = 4;
+    static_assert(D >= 5 && D <= 9, "v6 stages 5..9 levels per draw");
+    double *etop = smem_d;                      // exact top, levels 0..12
+    double *mtab = etop + TOPN;                 // [NTOP] approximate node mass, descent order
+    double *plo = mtab + NTOP;                  // [NTOP] approximate prefix inside a block of 64
+    double *phi = plo + NTOP;                   // [64]   approximate prefix of the blocks
+    double *s_misc = phi + 64;                  // [8]: rootA, total, min-root
+    double *sub_own = s_misc + 8;
+    double *sub_pref = sub_own + SUBN;          // [NBUF][BUFN]
+    double *o_prio = sub_pref + NBUF * BUFN;    // [RING]
+    int *o_slot = reinterpret_cast<int *>(o_prio + RING); // [RING]
+    int *hist = o_slot + RING;                  // [HIST] descent-order index of draw k's node
+    int *q_node = hist + HIST;                  // [Q] ascent queue
+    int *q_rel = q_node + Q;
+    int *q_buf = q_rel + Q;
+    int *flags = q_buf + Q;                     // [32]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(flags + 32);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 32; i++) flags[i] = -1;
+        flags[F_MAIN] = 0;
+        flags[F_ASC] = 0;
+        flags[F_ASCR] = 0;
+        flags[F_PUB] = 0;
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_expect_tx(bar, TOPN * 8);
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            bulk_g2s(etop + c * (TOPN / 4), a.sum + c * (TOPN / 4), TOPN * 2, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const long long mask = a.nslots - 1;
+    const long long npop = a.st->npop;
+    const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
+    const int oflip = older == 2 ? 0 : NTOP / 2; // descent order o <-> node 4096 + (o ^ oflip)
+    // ---- the approximate tables, from the exact top
+    for (int o = threadIdx.x; o < NTOP; o += blockDim.x) mtab[o] = etop[NTOP + (o ^ oflip)];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        double run = 0.0;
+        const int b = threadIdx.x;
+        for (int i = 0; i < 64; i++) {
+            plo[64 * b + i] = run;
+            run += mtab[64 * b + i];
+        }
+    } else if (threadIdx.x == 64) {
+        double run = 0.0;
+        for (int b = 0; b < 64; b++) {
+            phi[b] = run;
+            run += etop[64 + (b ^ (oflip >> 6))]; // level-6 nodes = sums of 64 level-12 nodes
+        }
+    }
+    __syncthreads();
+
+    const uint64_t pol = policy_evict_last();
+    const double2 *sum2 = reinterpret_cast<const double2 *>(a.sum);
+    const double root0 = etop[1];
+    if (threadIdx.x == 0) s_misc[0] = root0;
+    // decision margin (see the header comment / DESIGN.md)
+    const double eps = root0 * (double)(a.n + 64) * 1.4210854715202004e-14 /* 2^-46 */ *
+                       (a.dbg_eps_scale > 0.0 ? a.dbg_eps_scale : 1.0);
+    __syncthreads();
+
+    if ((warp & 3) == 0 && (warp >> 2) < NSCOUT) {
+        // ------------------------------ scouts -------------------------------
+        const double pbar = root0 / (double)(a.st->napp - npop); // expected mass per draw
+        for (int k = warp >> 2; k < a.n; k += NSCOUT) {
+            const double uk = a.u[k];
+            const int b = k % NBUF;
+            int m;
+            while ((m = ld_acquire_smem(&flags[F_MAIN])) < k - LAG ||
+                   ld_acquire_smem(&flags[F_ASCR]) < k - NBUF + 1)
+                __nanosleep(32);
+            // ---- prediction (any error only costs a slow draw): search the tables
+            double pos = uk * (s_misc[0] - (double)(k - m) * pbar);
+            int blk = __popc(__ballot_sync(0xffffffffu, pos >= phi[lane])) +
+                      __popc(__ballot_sync(0xffffffffu, pos >= phi[lane + 32])) - 1;
+            blk = blk < 0 ? 0 : blk;
+            pos -= phi[blk];
+            int w = __popc(__ballot_sync(0xffffffffu, pos >= plo[64 * blk + lane])) +
+                    __popc(__ballot_sync(0xffffffffu, pos >= plo[64 * blk + lane + 32])) - 1;
+            w = w < 0 ? 0 : w;
+            const int ord = 64 * blk + w;
+            const unsigned unode = (unsigned)(NTOP + (ord ^ oflip));
+            const int seen = ld_acquire_smem(&flags[F_ASC]);
+            double *dst = sub_pref + b * BUFN;
+            // internal levels: pair q = children of relative node q (q < NLEAF / 2), coalesced
+            double2 ipair[INIT];
+#pragma unroll
+            for (int it = 0; it < INIT; it++) {
+                int q = lane + 32 * it;
+                q = q < 1 ? 1 : (q > IPAIRS ? IPAIRS : q);
+                const int dq = 31 - __clz(q);
+                ipair[it] = ld_tree_pair(sum2 + ((unode << dq) + (unsigned)(q - (1 << dq))), pol);
+            }
+            // leaves: this lane's PER consecutive ones (PER / 2 pairs, PER = 1: half a pair)
+            constexpr int LP = PER >= 2 ? PER / 2 : 1;
+            double2 lpair[LP];
+            const double2 *leaf2 = sum2 + ((size_t)unode << (D - 1)); // pair p = leaves 2p, 2p+1
+#pragma unroll
+            for (int j = 0; j < LP; j++)
+                lpair[j] = ld_tree_pair(leaf2 + (PER >= 2 ? lane * LP + j : lane / 2), pol);
+#pragma unroll
+            for (int it = 0; it < INIT; it++) {
+                int q = lane + 32 * it;
+                q = q < 1 ? 1 : (q > IPAIRS ? IPAIRS : q);
+                reinterpret_cast<double2 *>(dst)[q] = ipair[it];
+            }
+            // running sums: start of this lane's block = exclusive scan of the block totals
+            double lf[PER];
+            if constexpr (PER >= 2) {
+#pragma unroll
+                for (int j = 0; j < LP; j++) {
+                    lf[2 * j] = lpair[j].x;
+                    lf[2 * j + 1] = lpair[j].y;
+                }
+            } else {
+                lf[0] = (lane & 1) ? lpair[0].y : lpair[0].x;
+            }
+            double bs = 0.0;
+#pragma unroll
+            for (int i = 0; i < PER; i++) bs += lf[i];
+            double incl = bs;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            double run = incl - bs;
+            dst[O_QB + lane] = run;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                dst[O_LT + i * 33 + lane] = lf[i];
+                dst[O_QT + i * 33 + lane] = run;
+                run += lf[i];
+            }
+            if (lane == 31) dst[O_QB + 32] = run;
+            __syncwarp();
+            if (lane == 0) {
+                flags[F_ORD + b] = ord;
+                flags[F_SEEN + b] = seen;
+                st_release_smem(&flags[F_READY + b], k);
+            }
+            __syncwarp();
+        }
+    } else if (warp == V6_W_MAIN) {
+        // ------------------------------- main --------------------------------
+        if (lane == 0) {
+            const double mroot = a.mn[1]; // priority_mins.min(), :59
+            a.st->last_total = root0;     // priority_sums.sum(), :58
+            a.st->last_min = mroot;
+            a.st->last_n = a.n;
+            s_misc[1] = root0;
+            s_misc[2] = mroot;
+        }
+        double rootA = root0;
+        int nfast = 0, nslow = 0;
+        for (int k0 = 0; k0 < a.n; k0 += CHUNK) {
+            const double u_lane = (k0 + lane < a.n) ? a.u[k0 + lane] : 0.0;
+            const int kend = (a.n - k0 < CHUNK) ? a.n - k0 : CHUNK;
+            while (ld_acquire_smem(&flags[F_PUB]) < k0 + CHUNK - RING) __nanosleep(32);
+            for (int kk = 0; kk < kend; kk++) {
+                const int k = k0 + kk;
+                const double uk = __shfl_sync(0xffffffffu, u_lane, kk);
+                const int b = k % NBUF;
+                int ord = 0, rel = 1;
+                double prio = 0.0;
+                bool fast = false;
+                // ---- wait (bounded) for the scout's staging of draw k
+                int rs = ld_acquire_smem(&flags[F_READY + b]);
+                for (int spin = 0; rs != k && spin < 48; spin++)
+                    rs = ld_acquire_smem(&flags[F_READY + b]);
+                if (rs == k && !(a.dbg_slow_every > 0 && k % a.dbg_slow_every == 0)) {
+                    const int o = flags[F_ORD + b];
+                    const int seen = flags[F_SEEN + b];
+                    // draws not yet applied to the exact tree when the copy was taken
+                    const int j = seen + lane;
+                    const bool clash = (j < k) && hist[j % HIST] == o;
+                    const bool conflict = __any_sync(0xffffffffu, clash) || (k - seen > 32);
+                    // position inside the node: u * root minus everything before it
+                    const double pos = (rootA * uk - phi[o >> 6]) - plo[o];
+                    const double *sub = sub_pref + b * BUFN;
+                    bool safe = !conflict && pos > eps && pos < mtab[o] - eps;
+                    // two 32-way compares against the running sums of the leaves
+                    int blk = __popc(__ballot_sync(0xffffffffu, pos >= sub[O_QB + lane])) - 1;
+                    blk = blk < 0 ? 0 : blk;
+                    int w = 0;
+                    if constexpr (PER > 1) {
+                        const unsigned c2 = __ballot_sync(
+                            0xffffffffu, pos >= sub[O_QT + (lane & (PER - 1)) * 33 + blk]);
+                        w = __popc(c2 & ((1u << PER) - 1u)) - 1;
+                        w = w < 0 ? 0 : w;
+                    }
+                    const double lo = sub[O_QT + w * 33 + blk];
+                    const double hi = (w + 1 < PER) ? sub[O_QT + (w + 1) * 33 + blk]
+                                                    : sub[O_QB + blk + 1];
+                    safe = safe && (pos - lo > eps) && (hi - pos > eps);
+                    if (safe) {
+                        fast = true;
+                        ord = o;
+                        rel = NLEAF + PER * blk + w;
+                        prio = sub[O_LT + w * 33 + blk];
+                        nfast++;
+                    }
+                }
+                int node;
+                if (!fast) {
+                    // ---- slow path: the reference's arithmetic on the exact tree
+                    nslow++;
+                    while (ld_acquire_smem(&flags[F_ASC]) < k) {
+                    }
+                    double pos = __dmul_rn(etop[1], uk); // np.random.uniform(0.0, root), :302
+                    node = older;
+                    {
+                        const double left = etop[older];
+                        if (!(pos < left)) {
+                            pos = __dsub_rn(pos, left);
+                            node = older ^ 1;
+                        }
+                    }
+                    spec_descend<T - 2, FMA>(etop, node, pos, lane); // level 1 -> 12
+                    const unsigned unode = (unsigned)node;
+#pragma unroll
+                    for (int it = 0; it < NIT; it++) {
+                        int q = lane + 32 * it;
+                        q = q < 1 ? 1 : (q > PAIRS ? PAIRS : q);
+                        const int dq = 31 - __clz(q);
+                        reinterpret_cast<double2 *>(sub_own)[q] =
+                            ld_tree_pair(sum2 + ((unode << dq) + (unsigned)(q - (1 << dq))), pol);
+                    }
+                    __syncwarp();
+                    rel = 1;
+                    spec_descend<D, FMA>(sub_own, rel, pos, lane);
+                    prio = sub_own[rel];
+                    ord = (node - NTOP) ^ oflip;
+                } else {
+                    node = NTOP + (ord ^ oflip);
+                }
+                // ---- hand the draw to the ascent warp and the publisher
+                while (ld_acquire_smem(&flags[F_ASCR]) < k - Q + 1) {
+                }
+                rootA = rootA - prio;
+                if (lane == 0) {
+                    q_node[k % Q] = node;
+                    q_rel[k % Q] = rel;
+                    q_buf[k % Q] = fast ? b : NBUF;
+                    hist[k % HIST] = ord;
+                    const unsigned leafnode = ((unsigned)node << D) + (unsigned)(rel - (1 << D));
+                    o_slot[k % RING] = (int)(leafnode - (unsigned)a.nslots);
+                    o_prio[k % RING] = prio;
+                    mtab[ord] = mtab[ord] - prio;
+                    s_misc[0] = rootA;
+                }
+                // ---- approximate update: everything after the drawn node, all at once
+                {
+                    const int base = ord & ~63, within = ord & 63, bk = ord >> 6;
+                    if (lane > within) plo[base + lane] = plo[base + lane] - prio;
+                    if (lane + 32 > within) plo[base + lane + 32] = plo[base + lane + 32] - prio;
+                    if (lane > bk) phi[lane] = phi[lane] - prio;
+                    if (lane + 32 > bk) phi[lane + 32] = phi[lane + 32] - prio;
+                }
+                __syncwarp();
+                if (lane == 0) st_release_smem(&flags[F_MAIN], k + 1);
+            }
+        }
+        if (lane == 0) a.st->pad = (nfast & 0xffff) | (nslow << 16); // fast draws, slow draws
+    } else if (warp == V6_W_ASC) {
+        // --------------- ascent: _write(ix, 0.0) on the exact tree ---------------
+        for (int k = 0; k < a.n; k++) {
+            while (ld_acquire_smem(&flags[F_MAIN]) <= k) __nanosleep(20);
+            const int node = q_node[k % Q];
+            const int rel = q_rel[k % Q];
+            const int bid = q_buf[k % Q];
+            const double *sub = bid < NBUF ? sub_pref + bid * BUFN : sub_own;
+            const unsigned unode = (unsigned)node;
+            double sib[D + T - 1];
+            {
+                // the sibling leaf: transposed array of a staged buffer, plain layout of sub_own
+                const int e = (rel - NLEAF) ^ 1;
+                sib[0] = bid < NBUF ? sub[O_LT + (e % PER) * 33 + e / PER] : sub[rel ^ 1];
+            }
+#pragma unroll
+            for (int j = 1; j < D; j++) sib[j] = sub[(rel >> j) ^ 1];
+#pragma unroll
+            for (int j = 0; j < T - 1; j++) sib[D + j] = etop[(node >> j) ^ 1];
+            const unsigned leafnode = (unode << D) + (unsigned)(rel - (1 << D));
+            double v = 0.0;
+            if (lane == 0) st_tree(a.sum + leafnode, 0.0, pol);
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                v = __dadd_rn(v, sib[j]);
+                if (lane == 0) {
+                    if (j + 1 < D) {
+                        const int dp = D - j - 1;
+                        const unsigned p = (unsigned)(rel >> (j + 1));
+                        st_tree(a.sum + ((unode << dp) + (p - (1u << dp))), v, pol);
+                    } else {
+                        etop[node] = v;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < T - 1; j++) {
+                v = __dadd_rn(v, sib[D + j]);
+                if (lane == 0) etop[node >> (j + 1)] = v;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // inputs consumed: a plain store ordered after the loads that fed the chain
+                *reinterpret_cast<volatile int *>(&flags[F_ASCR]) = k + 1;
+                // visibility of the global stores: every ASC_BATCH draws, and whenever
+                // the main warp has nothing more queued (it may be waiting for us)
+                if ((k + 1) % ASC_BATCH == 0 || k + 1 == a.n ||
+                    *reinterpret_cast<volatile int *>(&flags[F_MAIN]) == k + 1)
+                    st_release_smem(&flags[F_ASC], k + 1);
+            }
+            __syncwarp();
+        }
+    } else if (warp == V6_W_PUB) {
+        // ----------------------------- publisher -----------------------------
+        double total = 0.0, mroot = 0.0, bmin = INFINITY;
+        const double len = (double)(a.st->napp - npop);
+        for (int k0 = 0; k0 < a.n; k0 += CHUNK) {
+            const int kend = (a.n - k0 < CHUNK) ? a.n : k0 + CHUNK;
+            while (ld_acquire_smem(&flags[F_MAIN]) < kend) __nanosleep(200);
+            if (k0 == 0) {
+                total = s_misc[1];
+                mroot = s_misc[2];
+            }
+            const int k = k0 + lane;
+            if (k < kend) {
+                const long long slot = o_slot[k % RING];
+                const double prio = o_prio[k % RING];
+                a.slots_out[k] = (int32_t)slot;
+                a.prio_out[k] = prio;
+                if (a.index_out) a.index_out[k] = (slot - npop) & mask;
+                if (a.prio_user) a.prio_user[k] = prio;
+                const double p = prio / total;
+                if (a.prob) a.prob[k] = p;
+                bmin = fmin(bmin, p);
+                if (a.weight && a.norm != B2RL_NORM_BATCH)
+                    a.weight[k] = is_weight(p, mroot / total, len, a.beta, a.norm);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (a.ready) st_release_gpu(a.ready, a.seq_base | (unsigned long long)kend);
+                st_release_smem(&flags[F_PUB], kend);
+            }
+            __syncwarp();
+        }
+        if (a.weight && a.norm == B2RL_NORM_BATCH) {
+            for (int o = 16; o > 0; o >>= 1) bmin = fmin(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+            for (int k = lane; k < a.n; k += 32)
+                a.weight[k] = is_weight(a.prio_out[k] / total, bmin, len, a.beta, a.norm);
+        }
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            bulk_s2g(a.sum + c * (TOPN / 4), etop + c * (TOPN / 4), TOPN * 2);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
 }

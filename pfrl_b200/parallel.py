@@ -71,6 +71,18 @@ class GradSync:
             self._buckets[key] = b
         return b
 
+    def all_ready(self, flag):
+        """True iff `flag` is true on EVERY rank (all-reduce MIN of one scalar).  The
+        replay updater calls it at update opportunities until it returns True once, so
+        that all ranks take their first (and every later) optimizer step together."""
+        if world_size() == 1:
+            return bool(flag)
+        dev = (torch.device("cuda", torch.cuda.current_device())
+               if dist.get_backend() == "nccl" else torch.device("cpu"))
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t.item()))
+
     def __call__(self, module):
         w = world_size()
         if w == 1:

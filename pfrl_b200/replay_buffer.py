@@ -103,12 +103,28 @@ class ReplayUpdater(object):
         self.n_times_update = n_times_update
         self.replay_start_size = replay_start_size
         self.update_interval = update_interval
+        # data-parallel runs (parallel.GradSync): the agent that owns this updater; every
+        # update ends in a gradient all-reduce, so all ranks must update at the SAME
+        # iterations although their replay shards cross replay_start_size at different
+        # ones (n-step windows depend on each rank's episode boundaries)
+        self.agent = None
+        self._all_ranks_ready = False
 
     def update_if_necessary(self, iteration):
-        if len(self.replay_buffer) < self.replay_start_size:
-            return False
-        if iteration % self.update_interval != 0:
-            return False
+        ready = len(self.replay_buffer) >= self.replay_start_size
+        gs = getattr(self.agent, "grad_sync", None)
+        if gs is None:
+            if not ready or iteration % self.update_interval != 0:
+                return False
+        else:
+            # `iteration` advances identically on every rank, so this collective is
+            # entered by all of them or by none; once every shard is ready it stays so
+            if iteration % self.update_interval != 0:
+                return False
+            if not self._all_ranks_ready:
+                self._all_ranks_ready = gs.all_ready(ready)
+            if not self._all_ranks_ready:
+                return False
         for _ in range(self.n_times_update):
             self.update_func(self.replay_buffer.sample(self.batchsize))
         return True

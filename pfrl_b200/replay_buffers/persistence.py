@@ -6,28 +6,69 @@ import numpy as np
 import torch
 
 
+class _FramePool:
+    """Frames of frame-stacked (LazyFrames) observations, stored once: consecutive
+    observations share all but one frame, so the archive of a 1 M-transition Atari buffer
+    is ~7 GB of frames + index rows instead of 56 GB of stacked observations."""
+
+    def __init__(self):
+        self.ids = {}
+        self.frames = []
+
+    def index(self, stacked, stack):
+        """stacked: [m, stack * c, ...] -> int64 [m, stack] of frame ids."""
+        m = stacked.shape[0]
+        fr = stacked.reshape((m, stack, -1))
+        out = np.empty((m, stack), dtype=np.int64)
+        for i in range(m):
+            for j in range(stack):
+                key = fr[i, j].tobytes()
+                k = self.ids.get(key)
+                if k is None:
+                    k = len(self.frames)
+                    self.ids[key] = k
+                    self.frames.append(fr[i, j].copy())
+                out[i, j] = k
+        return out
+
+
 def save_buffer(buf, filename):
+    if getattr(buf, "_waiting", False):
+        # between sample() and update_errors() the sampled leaves are zero in the sum
+        # tree (collections/prioritized.py:98-116); the reference pickles whatever is
+        # there and fails on load, we refuse up front
+        raise RuntimeError("cannot save a prioritised buffer between sample() and "
+                           "update_errors(): the sampled priorities are not restored yet")
     buf._flush()
     n = len(buf)
-    meta = dict(n=n, num_steps=buf.num_steps, prioritized=buf._prioritized)
+    lay = buf.layout
+    lazy = bool(lay is not None and lay.lazy and not lay.on_device)
+    meta = dict(n=n, num_steps=buf.num_steps, prioritized=buf._prioritized, format=2,
+                lazy=int(lazy), stack=int(lay.stack) if lay is not None else 1)
     if n == 0:
         np.savez(filename if str(filename).endswith(".npz") else open(filename, "wb"), **meta)
         return
     from pfrl_b200.replay_buffers.device_buffer import DeviceExperiences
 
     chunks = {k: [] for k in ("state", "next_state", "action", "step_rewards", "len", "term")}
+    pool = _FramePool() if lazy else None
     for lo in range(0, n, 4096):
         m = min(4096, n - lo)
         idx = torch.arange(lo, lo + m, dtype=torch.int64, device=buf.device)
         out = buf._gather(DeviceExperiences(buf, m, index=idx), 1.0, None, raw=True,
                           want_steps=True)
-        chunks["state"].append(out["state"].cpu().numpy())
-        chunks["next_state"].append(out["next_state"].cpu().numpy())
+        st, ns = out["state"].cpu().numpy(), out["next_state"].cpu().numpy()
+        if lazy:  # frame ids instead of stacked observations
+            st, ns = pool.index(st, lay.stack), pool.index(ns, lay.stack)
+        chunks["state"].append(st)
+        chunks["next_state"].append(ns)
         chunks["action"].append(out["action"].cpu().numpy())
         chunks["step_rewards"].append(out["step_rewards"].cpu().numpy())
         chunks["len"].append(out["len"].cpu().numpy())
         chunks["term"].append(out["is_state_terminal"].cpu().numpy())
     arrays = {k: np.concatenate(v) for k, v in chunks.items()}
+    if lazy:
+        arrays["frames"] = np.stack(pool.frames).reshape((len(pool.frames),) + tuple(lay.part_shape))
     if buf._prioritized:
         arrays["priority"] = buf.store.read_priorities()
         arrays["max_priority"] = np.float64(buf.store.info()["max_priority"])
@@ -87,11 +128,26 @@ def load_buffer(buf, filename):
     assert int(z["num_steps"]) == buf.num_steps
     pr = z.get("priority")
 
+    lazy = bool(int(z.get("lazy", 0)))
+    if lazy:
+        # the observations come back as LazyFrames over SHARED frame objects: the store
+        # takes every frame once (identity de-duplication) and the layout stays the
+        # frame-stacked one, so appending LazyFrames after load() works
+        from pfrl_b200.utils.lazy_frames import LazyFrames
+
+        frames = [f for f in z["frames"]]
+
+        def obs(row):
+            return LazyFrames([frames[int(i)] for i in row], stack_axis=0)
+    else:
+        def obs(row):
+            return row
+
     def records():
         for k in range(n):
             L = int(z["len"][k])
-            yield (z["state"][k], z["next_state"][k], z["action"][k], z["step_rewards"][k][:L],
-                   z["term"][k], None if pr is None else pr[k])
+            yield (obs(z["state"][k]), obs(z["next_state"][k]), z["action"][k],
+                   z["step_rewards"][k][:L], z["term"][k], None if pr is None else pr[k])
 
     mp = z.get("max_priority")
     _restore(buf, records(), None if mp is None else float(mp))

@@ -11,7 +11,7 @@ def copy_param(target_link, source_link):
 def soft_copy_param(target_link, source_link, tau):
     """Polyak averaging ``target = (1 - tau) * target + tau * source`` over
     floating state_dict entries; integer buffers are copied
-    (copy_param.py:9-22).  One fused multi-tensor launch on CUDA."""
+    (copy_param.py:9-22).  One launch for all tensors on CUDA (b2rl_polyak)."""
     tgt = target_link.state_dict()
     src = source_link.state_dict()
     f_t, f_s = [], []
@@ -23,7 +23,16 @@ def soft_copy_param(target_link, source_link, tau):
             f_s.append(sv)
         else:
             tv.copy_(sv)
-    if f_t:
+    if not f_t:
+        return
+    if all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and s.is_cuda
+           and s.dtype == torch.float32 and s.is_contiguous() for t, s in zip(f_t, f_s)):
+        # one launch for the whole network (csrc/sac.cu, K9), rounded like the
+        # reference's target.mul_(1 - tau); target.add_(tau * source)
+        from pfrl_b200.ops.sac import polyak_
+
+        polyak_(f_t, f_s, tau)
+    else:
         torch._foreach_mul_(f_t, 1.0 - tau)
         torch._foreach_add_(f_t, f_s, alpha=tau)
 

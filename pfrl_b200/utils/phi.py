@@ -26,6 +26,19 @@ class ScaleU8:
         return np.asarray(x, dtype=np.float32) * np.float32(self.b2rl_obs_scale)
 
 
+class RawU8:
+    """phi(x) = x for uint8 observations whose ``/ 255`` is folded into the network's
+    first layer (nn.fast_conv.NatureConv1 reads uint8 as float(x) * 1/255): the gather
+    writes bytes (2.6x less HBM traffic than f32 batches) and the
+    convolution expands them in shared memory.  Same numbers as ScaleU8 + f32 conv."""
+
+    b2rl_obs_mode = OBS_RAW
+    b2rl_obs_scale = 1.0
+
+    def __call__(self, x):
+        return np.asarray(x, dtype=np.uint8)
+
+
 class Identity:
     """phi(x) = x (already-float observations; raw byte copy on the device)."""
 

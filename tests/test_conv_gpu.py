@@ -67,3 +67,65 @@ def test_conv1_speed_report():
         cudnn = timeit(lambda: F.conv2d(x, conv.weight, conv.bias, stride=4))
     print("conv1 fwd B=512: ours %.1f us, cuDNN fp32 %.1f us" % (ours, cudnn))
     assert ours < cudnn
+
+
+@pytest.mark.parametrize("n", [1, 5, 149, 512])
+def test_conv1_on_uint8_images_is_bit_identical_to_the_f32_path(n):
+    """phi = x / 255 folded into the layer (b2rl_conv_nature1_fwd_u8): same bits as the
+    ScaleU8 gather output fed to b2rl_conv_nature1_fwd, same weight gradient."""
+    from pfrl_b200.nn.fast_conv import NatureConv1
+    from pfrl_b200.utils.phi import ScaleU8
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(7 + n)
+    conv = NatureConv1().cuda()
+    x8 = torch.randint(0, 256, (n, 4, 84, 84), dtype=torch.uint8, device="cuda")
+    scale = ScaleU8().b2rl_obs_scale
+    assert scale == conv.input_scale
+    xf = x8.to(torch.float32) * scale          # what the U8_TO_F32 gather writes
+    out8, outf = conv(x8), conv(xf)
+    assert torch.equal(out8, outf)
+    g = torch.randn_like(out8)
+    conv.zero_grad()
+    out8.backward(g)
+    gw8 = conv.weight.grad.clone()
+    conv.zero_grad()
+    outf.backward(g)
+    assert torch.equal(gw8, conv.weight.grad)
+
+
+def test_rainbow_update_with_byte_batches_equals_f32_batches():
+    """RawU8 (bytes out of the replay gather, / 255 inside conv1) trains exactly like
+    ScaleU8 (f32 batches): same parameters after a few prioritised updates."""
+    import numpy as np
+
+    from pfrl_b200 import agents, explorers, nn as pnn, q_functions
+    from pfrl_b200.replay_buffers import PrioritizedReplayBuffer
+    from pfrl_b200.utils.phi import RawU8, ScaleU8
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    params = []
+    for phi in (ScaleU8(), RawU8()):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        q = q_functions.DistributionalDuelingDQN(6, 51, -10, 10)
+        pnn.to_factorized_noisy(q, sigma_scale=0.5)
+        buf = PrioritizedReplayBuffer(2000, alpha=0.5, beta0=0.4, betasteps=100, num_steps=3,
+                                      normalize_by_max="memory")
+        rng = np.random.RandomState(1)
+        frames = rng.randint(0, 256, size=(604, 84, 84), dtype=np.uint8)
+        term = rng.rand(600) < 0.02
+        term[-1] = True
+        buf.append_trajectory(frames, rng.randint(0, 6, size=600).astype(np.int64),
+                              rng.randint(-1, 2, size=600).astype(np.float64), term)
+        agent = agents.CategoricalDoubleDQN(
+            q, torch.optim.Adam(q.parameters(), 6.25e-5, eps=1.5e-4), buf, gpu=0, gamma=0.99,
+            explorer=explorers.Greedy(), minibatch_size=32, replay_start_size=32,
+            target_update_interval=100, update_interval=1, batch_accumulator="mean", phi=phi)
+        torch.manual_seed(5)
+        for _ in range(6):
+            agent.update(buf.sample(32))
+        params.append([p.detach().clone() for p in agent.model.parameters()])
+    for a, b in zip(*params):
+        assert torch.equal(a, b)

@@ -34,3 +34,5 @@ test_protocol_asserts_like_reference = bufsuite.test_protocol_asserts_like_refer
 test_device_per_arbitrary_host_phi_and_dict_view = \
     bufsuite.test_device_per_arbitrary_host_phi_and_dict_view
 test_save_load_round_trip = bufsuite.test_save_load_round_trip
+test_lazyframes_buffer_saves_frames_once_and_accepts_appends_after_load = \
+    bufsuite.test_lazyframes_buffer_saves_frames_once_and_accepts_appends_after_load
