@@ -485,12 +485,20 @@ def main():
             one_pass()
         t1.record()
         barrier()
-        ph = (ctypes.c_uint64 * 4)()
+        ph = (ctypes.c_uint64 * 36)()
         _lib.check(L.b2rl_step_times(h, ph, stream))  # %globaltimer stamps of the last launch
         _lib.check(L.b2rl_per_flush(h, stream))
         return t0.elapsed_time(t1), {"write_back_us": ph[0] / 1e3, "sampling_us": ph[1] / 1e3,
                                      "gather_after_last_draw_us": ph[2] / 1e3,
-                                     "launch_us": ph[3] / 1e3}
+                                     "launch_us": ph[3] / 1e3,
+                                     **({"sampler_cycles_per_draw": {
+                                         "main_wait_scout": ph[4] / B, "main_decide": ph[5] / B,
+                                         "main_wait_queue": ph[6] / B, "main_loads": ph[7] / B,
+                                         "main_stores": ph[8] / B,
+                                         "scout0_wait": ph[12] / (B / 4), "scout0_predict_issue": ph[13] / (B / 4),
+                                         "scout0_arrive_sums_store": ph[14] / (B / 4),
+                                         "ascent_wait": ph[20] / B, "ascent_work": ph[21] / B}}
+                                        if ph[5] else {})}
 
     clocks = ClockSampler(local_rank)
     if rank == 0:

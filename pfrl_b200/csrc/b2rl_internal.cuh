@@ -121,6 +121,7 @@ unsigned b2rl_next_ticket();
 bool b2rl_use_v6(int levels);
 int b2rl_v6_slow_every();
 double b2rl_v6_eps_scale();
+int b2rl_v6_sleep_scale();
 
 // Apply a write-back registered with b2rl_per_defer_errors (no-op if none).
 int b2rl_flush_pending(b2rl_replay *h, cudaStream_t s);

@@ -283,9 +283,9 @@ static int create_impl(b2rl_replay *h)
     // [0] draws-ready counter of the fused step, [1] write-back-done stamp, [2] arrival counter
     B2RL_CUDA(cudaMalloc((void **)&h->ready_dev, 128));
     B2RL_CUDA(cudaMemset(h->ready_dev, 0, 128));
-    B2RL_CUDA(cudaMalloc((void **)&h->times_dev, 8 * (8 + 256)));
-    B2RL_CUDA(cudaMemset(h->times_dev, 0, 8 * (8 + 256)));
-    h->device_bytes += 128 + 8 * (8 + 256);
+    B2RL_CUDA(cudaMalloc((void **)&h->times_dev, 8 * (8 + 256 + 32)));
+    B2RL_CUDA(cudaMemset(h->times_dev, 0, 8 * (8 + 256 + 32)));
+    h->device_bytes += 128 + 8 * (8 + 256 + 32);
     B2RL_CUDA(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
     B2RL_CUDA(cudaGetLastError());
     B2RL_CUDA(cudaDeviceSynchronize());

@@ -131,6 +131,17 @@ int b2rl_v6_slow_every()
     return cached;
 }
 
+int b2rl_v6_sleep_scale()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("B2RL_V6_SLEEP");
+        cached = e ? atoi(e) : 1;
+        if (cached < 1) cached = 1;
+    }
+    return cached;
+}
+
 double b2rl_v6_eps_scale()
 {
     static double cached = -1.0;
@@ -156,7 +167,7 @@ static cudaError_t launch_exact_v6(const SampleArgs &a, cudaStream_t s)
 
 static cudaError_t launch_exact_deep(const SampleArgs &a, cudaStream_t s)
 {
-    if (b2rl_use_v6(a.levels)) return launch_exact_v6(a, s);
+    if (b2rl_use_v6(a.levels) && a.n <= 60000) return launch_exact_v6(a, s); // u16 draw ids
     switch (a.D) {
     case 1: return launch_deep<1>(a, s);
     case 2: return launch_deep<2>(a, s);
@@ -220,6 +231,8 @@ extern "C" int b2rl_per_sample(b2rl_replay *h, const double *u_host, int32_t n, 
     a.seq_base = 0;
     a.dbg_slow_every = b2rl_v6_slow_every();
     a.dbg_eps_scale = b2rl_v6_eps_scale();
+    a.dbg_sleep_scale = b2rl_v6_sleep_scale();
+    a.dbg_cycles = nullptr;
     if (mode == B2RL_SAMPLE_EXACT && a.D > 0) {
         B2RL_CUDA(launch_exact_deep(a, s));
     } else if (mode == B2RL_SAMPLE_EXACT) {

@@ -24,6 +24,7 @@
 // instructions and no registers -- and convert u8 -> f32 out of shared memory
 // into 512-byte-per-warp coalesced .cs stores.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tree_dev.cuh"
 
@@ -325,7 +326,7 @@ static cudaError_t launch_step(const StepArgs &a, int mode, int grid, size_t sme
         const size_t sm = sizeof(double) * ((size_t(1) << a.s.T) + 2);
         return launch_step_as<0, 1>(a, grid, mx(smem_other, sm), s);
     }
-    if (b2rl_use_v6(a.s.levels)) {
+    if (b2rl_use_v6(a.s.levels) && a.s.n <= 60000) {
         switch (a.s.levels - (V6_T - 1)) {
         case 5: return launch_step_as<5, 3>(a, grid, mx(smem_other, exact_v6_smem_bytes<5>()), s);
         case 6: return launch_step_as<6, 3>(a, grid, mx(smem_other, exact_v6_smem_bytes<6>()), s);
@@ -439,6 +440,15 @@ extern "C" int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *p, void *s
     a.s.seq_base = seq_base;
     a.s.dbg_slow_every = b2rl_v6_slow_every();
     a.s.dbg_eps_scale = b2rl_v6_eps_scale();
+    a.s.dbg_sleep_scale = b2rl_v6_sleep_scale();
+    {
+        static int want = -1; // B2RL_V6_CYCLES=1: clock64 sums per pipeline segment of the sampler
+        if (want < 0) {
+            const char *e = getenv("B2RL_V6_CYCLES");
+            want = (e && e[0] == '1') ? 1 : 0;
+        }
+        a.s.dbg_cycles = want ? (long long *)(h->times_dev + 8 + 256) : nullptr;
+    }
     // ---- deferred write-back of the previous sample
     a.upd_n = 0;
     if (h->pending) {
@@ -535,5 +545,9 @@ extern "C" int b2rl_step_times(b2rl_replay *h, uint64_t *out_ns, void *stream)
     out_ns[1] = t[2] - t[1];
     out_ns[2] = last > t[2] ? last - t[2] : 0;
     out_ns[3] = last - t[0];
+    // [4, 36): clock64 sums of the exact sampler's pipeline segments (B2RL_V6_CYCLES=1)
+    B2RL_CUDA(cudaMemcpyAsync(out_ns + 4, h->times_dev + 8 + 256, sizeof(uint64_t) * 32,
+                              cudaMemcpyDeviceToHost, s));
+    B2RL_CUDA(cudaStreamSynchronize(s));
     return B2RL_OK;
 }

@@ -47,6 +47,8 @@ struct SampleArgs {
     // path on every k-th draw / widen the decision margin; results must not change
     int dbg_slow_every;
     double dbg_eps_scale;
+    int dbg_sleep_scale; // env B2RL_V6_SLEEP: multiplies the helper warps' poll back-off
+    long long *dbg_cycles; // optional [32]: clock64 sums per pipeline segment (tools/v6_cycles.py)
 };
 
 // ---------------------------------------------------------------------------
@@ -962,93 +964,112 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
         __syncthreads();
         const int cnt = ctr[0];
         if (cnt == 0) continue; // uniform
-        // ---- rank sort by (slot, draw index); keys are distinct
-        for (int i = tid; i < cnt; i += nt) {
-            const unsigned key = keys[i];
-            int rank = 0;
-            for (int j = 0; j < cnt; j++) rank += keys[j] < key;
-            skeys[rank] = key;
-        }
-        __syncthreads();
-        // ---- unique leaves (last occurrence of a slot wins), compaction
-        const int ngroups = (cnt + 31) >> 5;
-        for (int g = warp; g < ngroups; g += nw) {
-            const int i = g * 32 + lane;
-            const bool w = i < cnt && (i == cnt - 1 || (skeys[i + 1] >> 16) != (skeys[i] >> 16));
-            const unsigned b = __ballot_sync(0xffffffffu, w);
-            if (lane == 0) ctr[2 + g] = __popc(b);
-        }
-        __syncthreads();
-        int m = 0;
-        for (int g = 0; g < ngroups; g++) m += ctr[2 + g];
-        for (int g = warp; g < ngroups; g += nw) {
-            const int i = g * 32 + lane;
-            const bool w = i < cnt && (i == cnt - 1 || (skeys[i + 1] >> 16) != (skeys[i] >> 16));
-            const unsigned b = __ballot_sync(0xffffffffu, w);
-            int base = 0;
-            for (int q = 0; q < g; q++) base += ctr[2 + q];
-            if (w) {
-                const int pos = base + __popc(b & ((1u << lane) - 1u));
-                const int lf = (st << lb) | (int)(skeys[i] >> 16);
-                leaf[pos] = lf;
-                if (a.nranges > 0) { // repair: the leaves are already in place
-                    vs[pos] = a.sum[a.nslots + lf];
-                    vm[pos] = a.mn[a.nslots + lf];
-                } else {
-                    const double p = prio_k[skeys[i] & 0xffffu];
-                    vs[pos] = p;
-                    vm[pos] = p;
-                }
-                runlen[pos] = 1;
-                lead[pos] = 1;
+        // A subtree usually gets a handful of the 512 leaves: one warp then does the rest
+        // with warp barriers only (no 512-thread barrier per level); a crowded subtree
+        // takes the whole CTA.
+        const bool solo = cnt <= 32;
+        const int wt = solo ? lane : tid;        // worker index / count inside the team
+        const int wn = solo ? 32 : nt;
+        const int ww = solo ? 0 : warp, wnw = solo ? 1 : nw;
+        const bool member = !solo || warp == 0;
+#define TEAM_SYNC()            \
+    do {                       \
+        if (solo)              \
+            __syncwarp();      \
+        else                   \
+            __syncthreads();   \
+    } while (0)
+        if (member) {
+            // ---- rank sort by (slot, draw index); keys are distinct
+            for (int i = wt; i < cnt; i += wn) {
+                const unsigned key = keys[i];
+                int rank = 0;
+                for (int j = 0; j < cnt; j++) rank += keys[j] < key;
+                skeys[rank] = key;
             }
-        }
-        __syncthreads();
-        // ---- leaves out, every sibling of every path inside the subtree in
-        if (a.nranges == 0)
-            for (int i = tid; i < m; i += nt) {
-                const long long ln = a.nslots + leaf[i];
-                a.sum[ln] = vs[i];
-                a.mn[ln] = vm[i];
+            TEAM_SYNC();
+            // ---- unique leaves (last occurrence of a slot wins), compaction
+            const int ngroups = (cnt + 31) >> 5;
+            for (int g = ww; g < ngroups; g += wnw) {
+                const int i = g * 32 + lane;
+                const bool w = i < cnt && (i == cnt - 1 || (skeys[i + 1] >> 16) != (skeys[i] >> 16));
+                const unsigned b = __ballot_sync(0xffffffffu, w);
+                if (lane == 0) ctr[2 + g] = __popc(b);
             }
-        for (int idx = tid; idx < m * lb; idx += nt) {
-            const int i = idx % m, s = idx / m;
-            const long long node = (a.nslots + leaf[i]) >> s;
-            sib_s[(size_t)s * UPD_MAX + i] = a.sum[node ^ 1];
-            sib_m[(size_t)s * UPD_MAX + i] = a.mn[node ^ 1];
-        }
-        __syncthreads();
-        // ---- level loop on shared memory (see tree_update_paths)
-        for (int s = 0; s < lb; s++) {
-            for (int i = tid; i < m; i += nt) {
-                if (!lead[i]) continue;
-                const long long node = (a.nslots + leaf[i]) >> s;
-                double ns, nm;
-                if ((node & 1) == 0) {
-                    const int j = i + runlen[i];
-                    if (j < m && ((a.nslots + leaf[j]) >> s) == node + 1) {
-                        ns = __dadd_rn(vs[i], vs[j]);
-                        nm = fmin(vm[i], vm[j]);
-                        runlen[i] += runlen[j];
+            TEAM_SYNC();
+            int m = 0;
+            for (int g = 0; g < ngroups; g++) m += ctr[2 + g];
+            for (int g = ww; g < ngroups; g += wnw) {
+                const int i = g * 32 + lane;
+                const bool w = i < cnt && (i == cnt - 1 || (skeys[i + 1] >> 16) != (skeys[i] >> 16));
+                const unsigned b = __ballot_sync(0xffffffffu, w);
+                int base = 0;
+                for (int q = 0; q < g; q++) base += ctr[2 + q];
+                if (w) {
+                    const int pos = base + __popc(b & ((1u << lane) - 1u));
+                    const int lf = (st << lb) | (int)(skeys[i] >> 16);
+                    leaf[pos] = lf;
+                    if (a.nranges > 0) { // repair: the leaves are already in place
+                        vs[pos] = a.sum[a.nslots + lf];
+                        vm[pos] = a.mn[a.nslots + lf];
                     } else {
-                        ns = __dadd_rn(vs[i], sib_s[(size_t)s * UPD_MAX + i]);
-                        nm = fmin(vm[i], sib_m[(size_t)s * UPD_MAX + i]);
+                        const double p = prio_k[skeys[i] & 0xffffu];
+                        vs[pos] = p;
+                        vm[pos] = p;
                     }
-                } else {
-                    if (i > 0 && ((a.nslots + leaf[i - 1]) >> s) == node - 1) {
-                        lead[i] = 0;
-                        continue;
-                    }
-                    ns = __dadd_rn(sib_s[(size_t)s * UPD_MAX + i], vs[i]);
-                    nm = fmin(sib_m[(size_t)s * UPD_MAX + i], vm[i]);
+                    runlen[pos] = 1;
+                    lead[pos] = 1;
                 }
-                vs[i] = ns;
-                vm[i] = nm;
-                a.sum[node >> 1] = ns;
-                a.mn[node >> 1] = nm;
             }
-            __syncthreads();
+            TEAM_SYNC();
+            // ---- leaves out, every sibling of every path inside the subtree in
+            if (a.nranges == 0)
+                for (int i = wt; i < m; i += wn) {
+                    const long long ln = a.nslots + leaf[i];
+                    a.sum[ln] = vs[i];
+                    a.mn[ln] = vm[i];
+                }
+            for (int idx = wt; idx < m * lb; idx += wn) {
+                const int i = idx % m, s = idx / m;
+                const long long node = (a.nslots + leaf[i]) >> s;
+                sib_s[(size_t)s * UPD_MAX + i] = a.sum[node ^ 1];
+                sib_m[(size_t)s * UPD_MAX + i] = a.mn[node ^ 1];
+            }
+            TEAM_SYNC();
+            // ---- level loop on shared memory (see tree_update_paths)
+            for (int s = 0; s < lb; s++) {
+                for (int i = wt; i < m; i += wn) {
+                    if (!lead[i]) continue;
+                    const long long node = (a.nslots + leaf[i]) >> s;
+                    double ns, nm;
+                    if ((node & 1) == 0) {
+                        const int j = i + runlen[i];
+                        if (j < m && ((a.nslots + leaf[j]) >> s) == node + 1) {
+                            ns = __dadd_rn(vs[i], vs[j]);
+                            nm = fmin(vm[i], vm[j]);
+                            runlen[i] += runlen[j];
+                        } else {
+                            ns = __dadd_rn(vs[i], sib_s[(size_t)s * UPD_MAX + i]);
+                            nm = fmin(vm[i], sib_m[(size_t)s * UPD_MAX + i]);
+                        }
+                    } else {
+                        if (i > 0 && ((a.nslots + leaf[i - 1]) >> s) == node - 1) {
+                            lead[i] = 0;
+                            continue;
+                        }
+                        ns = __dadd_rn(sib_s[(size_t)s * UPD_MAX + i], vs[i]);
+                        nm = fmin(sib_m[(size_t)s * UPD_MAX + i], vm[i]);
+                    }
+                    vs[i] = ns;
+                    vm[i] = nm;
+                    a.sum[node >> 1] = ns;
+                    a.mn[node >> 1] = nm;
+                }
+                TEAM_SYNC();
+            }
         }
+#undef TEAM_SYNC
+        __syncthreads(); // the team rejoins the CTA (uniform: cnt is the same for all)
     }
     // ---- max_priority (positive doubles order like their bit patterns), arrival
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1154,7 +1175,6 @@ static constexpr int V6_T = 13;
 static constexpr int V6_NSCOUT = 4;
 static constexpr int V6_LAG = 4;
 static constexpr int V6_NBUF = 6;
-static constexpr int V6_HIST = 64;
 static constexpr int V6_Q = 16;
 static constexpr int V6_NTOP = 1 << (V6_T - 1);  // 4096 level-12 nodes
 // Warp roles.  The issue arbiter of an SM sub-partition (warp id % 4) prefers its
@@ -1177,9 +1197,9 @@ template <int D>
 __host__ __device__ constexpr size_t exact_v6_smem_bytes()
 {
     // etop, M, P_lo, P_hi(64) + rootA + stat(2) + pad, sub_own, NBUF x staged buffer, o_prio
-    return sizeof(double) * ((size_t(1) << V6_T) + 2 * V6_NTOP + 72 + (size_t(2) << D) +
+    return sizeof(double) * ((size_t(1) << V6_T) + 2 * V6_NTOP + 80 + (size_t(2) << D) +
                              V6_NBUF * v6_buf_doubles(D) + EX_RING) +
-           sizeof(int) * (EX_RING + V6_HIST + 3 * V6_Q + 32) + 16;
+           sizeof(int) * (EX_RING + 3 * V6_Q + 32) + sizeof(unsigned short) * V6_NTOP + 16;
 }
 
 template <int D, bool FMA>
@@ -1200,15 +1220,14 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
     constexpr int INIT = (IPAIRS + 31) / 32;
     constexpr int CHUNK = 32;
     constexpr int NSCOUT = V6_NSCOUT, LAG = V6_LAG, NBUF = V6_NBUF, RING = EX_RING;
-    constexpr int HIST = V6_HIST, Q = V6_Q;
+    constexpr int Q = V6_Q;
     // F_ASC:  draws whose exact update is VISIBLE (global stores fenced), published in
     //         batches -- the fence waits for the L2 acknowledgement of the ascent's global
     //         stores and a MEMBAR holds up the SM's shared-memory pipe for everybody, so it
     //         must not be paid per draw;
     // F_ASCR: draws the ascent warp has finished READING the inputs of (relaxed, per draw):
     //         staged buffers and queue slots can be reused.
-    constexpr int F_READY = 0, F_ORD = 8, F_SEEN = 16, F_MAIN = 24, F_ASC = 25, F_PUB = 26,
-                  F_ASCR = 27;
+    constexpr int F_MAIN = 24, F_ASC = 25, F_PUB = 26, F_ASCR = 27;
     constexpr int ASC_BATCH = 4;
     static_assert(D >= 5 && D <= 9, "v6 stages 5..9 levels per draw");
     double *etop = smem_d;                      // exact top, levels 0..12
@@ -1216,16 +1235,20 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
     double *plo = mtab + NTOP;                  // [NTOP] approximate prefix inside a block of 64
     double *phi = plo + NTOP;                   // [64]   approximate prefix of the blocks
     double *s_misc = phi + 64;                  // [8]: rootA, total, min-root
-    double *sub_own = s_misc + 8;
+    // [NBUF] one word per staged buffer: draw << 32 | F_ASC seen << 12 | node (descent order)
+    unsigned long long *ready64 = reinterpret_cast<unsigned long long *>(s_misc + 8);
+    double *sub_own = s_misc + 16;
     double *sub_pref = sub_own + SUBN;          // [NBUF][BUFN]
     double *o_prio = sub_pref + NBUF * BUFN;    // [RING]
     int *o_slot = reinterpret_cast<int *>(o_prio + RING); // [RING]
-    int *hist = o_slot + RING;                  // [HIST] descent-order index of draw k's node
-    int *q_node = hist + HIST;                  // [Q] ascent queue
+    int *q_node = o_slot + RING;                // [Q] ascent queue
     int *q_rel = q_node + Q;
     int *q_buf = q_rel + Q;
     int *flags = q_buf + Q;                     // [32]
     uint64_t *bar = reinterpret_cast<uint64_t *>(flags + 32);
+    // 1 + index of the last draw of this launch that chose node o (0 = none): the conflict
+    // test "did a draw still in flight touch this subtree" is one load, no vote
+    unsigned short *lastd = reinterpret_cast<unsigned short *>(bar + 2);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 
@@ -1251,7 +1274,11 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
     const int older = ((npop & mask) >= (a.nslots >> 1)) ? 3 : 2;
     const int oflip = older == 2 ? 0 : NTOP / 2; // descent order o <-> node 4096 + (o ^ oflip)
     // ---- the approximate tables, from the exact top
-    for (int o = threadIdx.x; o < NTOP; o += blockDim.x) mtab[o] = etop[NTOP + (o ^ oflip)];
+    for (int o = threadIdx.x; o < NTOP; o += blockDim.x) {
+        mtab[o] = etop[NTOP + (o ^ oflip)];
+        lastd[o] = 0;
+    }
+    if (threadIdx.x < 8) ready64[threadIdx.x] = ~0ull;
     __syncthreads();
     if (threadIdx.x < 64) {
         double run = 0.0;
@@ -1271,6 +1298,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
 
     const uint64_t pol = policy_evict_last();
     const double2 *sum2 = reinterpret_cast<const double2 *>(a.sum);
+    const unsigned slp = a.dbg_sleep_scale > 0 ? (unsigned)a.dbg_sleep_scale : 1u;
     const double root0 = etop[1];
     if (threadIdx.x == 0) s_misc[0] = root0;
     // decision margin (see the header comment / DESIGN.md)
@@ -1281,13 +1309,16 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
     if ((warp & 3) == 0 && (warp >> 2) < NSCOUT) {
         // ------------------------------ scouts -------------------------------
         const double pbar = root0 / (double)(a.st->napp - npop); // expected mass per draw
+        long long c_wait = 0, c_fetch = 0, c_rest = 0;
         for (int k = warp >> 2; k < a.n; k += NSCOUT) {
+            const long long tc0 = clock64();
             const double uk = a.u[k];
             const int b = k % NBUF;
             int m;
             while ((m = ld_acquire_smem(&flags[F_MAIN])) < k - LAG ||
                    ld_acquire_smem(&flags[F_ASCR]) < k - NBUF + 1)
-                __nanosleep(32);
+                __nanosleep(32 * slp);
+            const long long tc1 = clock64();
             // ---- prediction (any error only costs a slow draw): search the tables
             double pos = uk * (s_misc[0] - (double)(k - m) * pbar);
             int blk = __popc(__ballot_sync(0xffffffffu, pos >= phi[lane])) +
@@ -1324,6 +1355,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                 reinterpret_cast<double2 *>(dst)[q] = ipair[it];
             }
             // running sums: start of this lane's block = exclusive scan of the block totals
+            const long long tc2 = clock64();
             double lf[PER];
             if constexpr (PER >= 2) {
 #pragma unroll
@@ -1354,11 +1386,23 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
             if (lane == 31) dst[O_QB + 32] = run;
             __syncwarp();
             if (lane == 0) {
-                flags[F_ORD + b] = ord;
-                flags[F_SEEN + b] = seen;
-                st_release_smem(&flags[F_READY + b], k);
+                const unsigned long long wv = ((unsigned long long)(unsigned)k << 32) |
+                                              ((unsigned long long)(unsigned)seen << 12) |
+                                              (unsigned long long)ord;
+                asm volatile("st.release.cta.shared.b64 [%0], %1;" ::"r"(smem_u32(&ready64[b])),
+                             "l"(wv)
+                             : "memory");
             }
             __syncwarp();
+            const long long tc3 = clock64();
+            c_wait += tc1 - tc0;
+            c_fetch += tc2 - tc1;   // prediction + issue of the loads + store of the internal levels
+            c_rest += tc3 - tc2;    // leaf loads arrive, running sums, stores, release
+        }
+        if (a.dbg_cycles && lane == 0 && warp == 0) {
+            a.dbg_cycles[8] = c_wait;
+            a.dbg_cycles[9] = c_fetch;
+            a.dbg_cycles[10] = c_rest;
         }
     } else if (warp == V6_W_MAIN) {
         // ------------------------------- main --------------------------------
@@ -1370,36 +1414,88 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
             s_misc[1] = root0;
             s_misc[2] = mroot;
         }
+        // The loop is software-pipelined around one measured fact: a shared-memory LOAD
+        // issued behind this warp's own STOREs waits 100-200 cycles for them to drain
+        // (ncu: three such load -> DADD pairs were 45 % of the draw).  So every draw issues
+        // ALL its loads first -- including the ones the NEXT draw needs -- and its stores
+        // last.  The next draw's table entries are therefore read before this draw's update
+        // is stored; the one missing update is applied in registers (ord_prev, p_prev).
         double rootA = root0;
         int nfast = 0, nslow = 0;
+        // prefetched state of the draw about to be decided
+        int pf_rs = -1, pf_o = 0, pf_seen = 0, pf_last = 0;
+        double pf_pre = 0.0, pf_mass = 0.0, pf_qb = 0.0;
+        bool pf_stale = false;      // read before the previous draw's stores
+        int ord_prev = -1;
+        double p_prev = 0.0;
+        long long c_ready = 0, c_decide = 0, c_queue = 0, c_loads = 0, c_stores = 0;
+        auto prefetch = [&](int k) {
+            const int b = k % NBUF;
+            unsigned long long wv;
+            asm volatile("ld.acquire.cta.shared.b64 %0, [%1];"
+                         : "=l"(wv)
+                         : "r"(smem_u32(&ready64[b]))
+                         : "memory");
+            pf_rs = (int)(wv >> 32);
+            pf_o = (int)(wv & (NTOP - 1));          // garbage unless pf_rs == k, but in range
+            pf_seen = (int)((wv >> 12) & 0xfffffu);
+            pf_pre = phi[pf_o >> 6] + plo[pf_o];
+            pf_mass = mtab[pf_o];
+            pf_last = lastd[pf_o];
+            pf_qb = sub_pref[b * BUFN + O_QB + lane];
+        };
+        if (a.n > 0) prefetch(0);
         for (int k0 = 0; k0 < a.n; k0 += CHUNK) {
             const double u_lane = (k0 + lane < a.n) ? a.u[k0 + lane] : 0.0;
             const int kend = (a.n - k0 < CHUNK) ? a.n - k0 : CHUNK;
             while (ld_acquire_smem(&flags[F_PUB]) < k0 + CHUNK - RING) __nanosleep(32);
             for (int kk = 0; kk < kend; kk++) {
                 const int k = k0 + kk;
+                const long long tm0 = clock64();
                 const double uk = __shfl_sync(0xffffffffu, u_lane, kk);
                 const int b = k % NBUF;
                 int ord = 0, rel = 1;
                 double prio = 0.0;
                 bool fast = false;
-                // ---- wait (bounded) for the scout's staging of draw k
-                int rs = ld_acquire_smem(&flags[F_READY + b]);
-                for (int spin = 0; rs != k && spin < 48; spin++)
-                    rs = ld_acquire_smem(&flags[F_READY + b]);
-                if (rs == k && !(a.dbg_slow_every > 0 && k % a.dbg_slow_every == 0)) {
-                    const int o = flags[F_ORD + b];
-                    const int seen = flags[F_SEEN + b];
-                    // draws not yet applied to the exact tree when the copy was taken
-                    const int j = seen + lane;
-                    const bool clash = (j < k) && hist[j % HIST] == o;
-                    const bool conflict = __any_sync(0xffffffffu, clash) || (k - seen > 32);
+                // ---- the scout's staging of draw k: prefetched, or wait for it (bounded)
+                if (pf_rs != k) {
+                    for (int spin = 0; spin < 48; spin++) {
+                        unsigned long long wv;
+                        asm volatile("ld.acquire.cta.shared.b64 %0, [%1];"
+                                     : "=l"(wv)
+                                     : "r"(smem_u32(&ready64[b]))
+                                     : "memory");
+                        if ((int)(wv >> 32) == k) break;
+                    }
+                    prefetch(k);
+                    pf_stale = false;
+                }
+                // this draw's prefetched state moves to locals; the NEXT draw's loads start now,
+                // behind no store of this warp, and overlap the whole decision below
+                const int c_rs = pf_rs, c_o = pf_o, c_seen = pf_seen, c_last = pf_last;
+                const double c_pre = pf_pre, c_mass = pf_mass, c_qb = pf_qb;
+                const bool c_stale = pf_stale;
+                if (k + 1 < a.n) {
+                    prefetch(k + 1);
+                    pf_stale = true;
+                }
+                const long long tm1 = clock64();
+                if (c_rs == k && !(a.dbg_slow_every > 0 && k % a.dbg_slow_every == 0)) {
+                    const int o = c_o;
+                    // a draw not yet applied to the exact tree when the copy was taken chose
+                    // the same node?  (draw j is recorded as j + 1; the previous draw may
+                    // still be missing from the table when the entry was read)
+                    const bool conflict = c_last > c_seen || (c_stale && ord_prev == o) ||
+                                          k - c_seen > 60000;
                     // position inside the node: u * root minus everything before it
-                    const double pos = (rootA * uk - phi[o >> 6]) - plo[o];
+                    double pre = c_pre;
+                    if (c_stale && ord_prev < o) pre -= p_prev; // the update not yet in the tables
+                    const double pos = rootA * uk - pre;
+                    const double mass = (c_stale && ord_prev == o) ? c_mass - p_prev : c_mass;
                     const double *sub = sub_pref + b * BUFN;
-                    bool safe = !conflict && pos > eps && pos < mtab[o] - eps;
+                    bool safe = !conflict && pos > eps && pos < mass - eps;
                     // two 32-way compares against the running sums of the leaves
-                    int blk = __popc(__ballot_sync(0xffffffffu, pos >= sub[O_QB + lane])) - 1;
+                    int blk = __popc(__ballot_sync(0xffffffffu, pos >= c_qb)) - 1;
                     blk = blk < 0 ? 0 : blk;
                     int w = 0;
                     if constexpr (PER > 1) {
@@ -1411,12 +1507,13 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                     const double lo = sub[O_QT + w * 33 + blk];
                     const double hi = (w + 1 < PER) ? sub[O_QT + (w + 1) * 33 + blk]
                                                     : sub[O_QB + blk + 1];
+                    const double pr = sub[O_LT + w * 33 + blk];
                     safe = safe && (pos - lo > eps) && (hi - pos > eps);
                     if (safe) {
                         fast = true;
                         ord = o;
                         rel = NLEAF + PER * blk + w;
-                        prio = sub[O_LT + w * 33 + blk];
+                        prio = pr;
                         nfast++;
                     }
                 }
@@ -1453,38 +1550,68 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                 } else {
                     node = NTOP + (ord ^ oflip);
                 }
-                // ---- hand the draw to the ascent warp and the publisher
-                while (ld_acquire_smem(&flags[F_ASCR]) < k - Q + 1) {
-                }
+                const long long tm2 = clock64();
+                // room in the ascent queue: Q entries, checked every fourth draw
+                if ((k & 3) == 0)
+                    while (ld_acquire_smem(&flags[F_ASCR]) < k - Q + 4) {
+                    }
+                const long long tm3 = clock64();
                 rootA = rootA - prio;
+                // ---- loads first: this draw's table entries
+                const int base = ord & ~63, within = ord & 63, bk = ord >> 6;
+                const double t_m = mtab[ord];
+                const double t_l0 = plo[base + lane], t_l1 = plo[base + lane + 32];
+                const double t_h0 = phi[lane], t_h1 = phi[lane + 32];
+                // ---- then the stores: ascent queue, publisher ring, approximate tables
+                const long long tm4 = clock64();
                 if (lane == 0) {
                     q_node[k % Q] = node;
                     q_rel[k % Q] = rel;
                     q_buf[k % Q] = fast ? b : NBUF;
-                    hist[k % HIST] = ord;
+                    lastd[ord] = (unsigned short)(k + 1);
                     const unsigned leafnode = ((unsigned)node << D) + (unsigned)(rel - (1 << D));
                     o_slot[k % RING] = (int)(leafnode - (unsigned)a.nslots);
                     o_prio[k % RING] = prio;
-                    mtab[ord] = mtab[ord] - prio;
+                    mtab[ord] = t_m - prio;
                     s_misc[0] = rootA;
                 }
-                // ---- approximate update: everything after the drawn node, all at once
-                {
-                    const int base = ord & ~63, within = ord & 63, bk = ord >> 6;
-                    if (lane > within) plo[base + lane] = plo[base + lane] - prio;
-                    if (lane + 32 > within) plo[base + lane + 32] = plo[base + lane + 32] - prio;
-                    if (lane > bk) phi[lane] = phi[lane] - prio;
-                    if (lane + 32 > bk) phi[lane + 32] = phi[lane + 32] - prio;
-                }
+                if (lane > within) plo[base + lane] = t_l0 - prio;
+                if (lane + 32 > within) plo[base + lane + 32] = t_l1 - prio;
+                if (lane > bk) phi[lane] = t_h0 - prio;
+                if (lane + 32 > bk) phi[lane + 32] = t_h1 - prio;
+                ord_prev = ord;
+                p_prev = prio;
                 __syncwarp();
-                if (lane == 0) st_release_smem(&flags[F_MAIN], k + 1);
+                // consumers read what LANE 0 stored above (queue, ring) after this flag; one
+                // thread's shared-memory stores are performed in order, so a plain store does
+                // what st.release did without the MEMBAR
+                if (lane == 0)
+                    asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&flags[F_MAIN])),
+                                 "r"(k + 1)
+                                 : "memory");
+                const long long tm5 = clock64();
+                c_ready += tm1 - tm0;
+                c_decide += tm2 - tm1;
+                c_queue += tm3 - tm2;
+                c_loads += tm4 - tm3;
+                c_stores += tm5 - tm4;
             }
+        }
+        if (a.dbg_cycles && lane == 0) {
+            a.dbg_cycles[0] = c_ready;
+            a.dbg_cycles[1] = c_decide;
+            a.dbg_cycles[2] = c_queue;
+            a.dbg_cycles[3] = c_loads;
+            a.dbg_cycles[4] = c_stores;
         }
         if (lane == 0) a.st->pad = (nfast & 0xffff) | (nslow << 16); // fast draws, slow draws
     } else if (warp == V6_W_ASC) {
         // --------------- ascent: _write(ix, 0.0) on the exact tree ---------------
+        long long c_await = 0, c_awork = 0;
         for (int k = 0; k < a.n; k++) {
-            while (ld_acquire_smem(&flags[F_MAIN]) <= k) __nanosleep(20);
+            const long long ta0 = clock64();
+            while (ld_acquire_smem(&flags[F_MAIN]) <= k) __nanosleep(20 * slp);
+            const long long ta1 = clock64();
             const int node = q_node[k % Q];
             const int rel = q_rel[k % Q];
             const int bid = q_buf[k % Q];
@@ -1507,13 +1634,10 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
             for (int j = 0; j < D; j++) {
                 v = __dadd_rn(v, sib[j]);
                 if (lane == 0) {
-                    if (j + 1 < D) {
-                        const int dp = D - j - 1;
-                        const unsigned p = (unsigned)(rel >> (j + 1));
-                        st_tree(a.sum + ((unode << dp) + (p - (1u << dp))), v, pol);
-                    } else {
+                    if (j + 1 < D)
+                        st_tree(a.sum + (leafnode >> (j + 1)), v, pol); // heap parent chain
+                    else
                         etop[node] = v;
-                    }
                 }
             }
 #pragma unroll
@@ -1532,6 +1656,12 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                     st_release_smem(&flags[F_ASC], k + 1);
             }
             __syncwarp();
+            c_await += ta1 - ta0;
+            c_awork += clock64() - ta1;
+        }
+        if (a.dbg_cycles && lane == 0) {
+            a.dbg_cycles[16] = c_await;
+            a.dbg_cycles[17] = c_awork;
         }
     } else if (warp == V6_W_PUB) {
         // ----------------------------- publisher -----------------------------
@@ -1539,7 +1669,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
         const double len = (double)(a.st->napp - npop);
         for (int k0 = 0; k0 < a.n; k0 += CHUNK) {
             const int kend = (a.n - k0 < CHUNK) ? a.n : k0 + CHUNK;
-            while (ld_acquire_smem(&flags[F_MAIN]) < kend) __nanosleep(200);
+            while (ld_acquire_smem(&flags[F_MAIN]) < kend) __nanosleep(200 * slp);
             if (k0 == 0) {
                 total = s_misc[1];
                 mroot = s_misc[2];

@@ -8,7 +8,7 @@ run() { local name=$1 to=$2; shift 2; echo "== $name" | tee -a gpurun_out/c9.log
 run default 900 python -m pytest $T -x -q
 B2RL_V6_SLOW_EVERY=3 run slow3 600 python -m pytest $T -x -q
 B2RL_V6_EPS_SCALE=1e7 run eps1e7 600 python -m pytest tests/test_per_gpu.py tests/test_headline_shapes_gpu.py -x -q
-run new 900 python -m pytest tests/test_conv_gpu.py tests/test_train_driver_gpu.py tests/test_agent_traces_gpu.py tests/test_sac_kernels_gpu.py -q
+run new 900 python -m pytest tests/test_conv_gpu.py tests/test_train_driver_gpu.py -q
 run benchq 600 python bench.py --no-cpu-baseline --no-rainbow --no-secondary --steps 8 --warmup 2
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on --warp-sampling-interval 0 \
   -k regex:"k_sample_exact_v6" -s 4 -c 1 -o gpurun_out/r02_v6e \
