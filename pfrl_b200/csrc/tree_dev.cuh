@@ -1125,6 +1125,15 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
     }
 }
 
+#ifndef B2RL_V6_PROFILE
+#define B2RL_V6_PROFILE 0 // 1: clock64 sums per pipeline segment (b2rl_step_times [4..35])
+#endif
+#if B2RL_V6_PROFILE
+#define V6_CLK() clock64()
+#else
+#define V6_CLK() 0ll
+#endif
+
 // ===========================================================================
 // EXACT sampler v6: decisions on approximate prefix tables, proofs by margin,
 // the exact re-reduction trails on its own warp.
@@ -1183,14 +1192,16 @@ static constexpr int V6_NTOP = 1 << (V6_T - 1);  // 4096 level-12 nodes
 static constexpr int V6_W_MAIN = 3, V6_W_ASC = 1, V6_W_PUB = 2; // scouts: warps 0, 4, 8, 12
 static constexpr int V6_THREADS = 512;
 
-// One staged subtree: [internal nodes, relative heap index < 2^D][LT: leaves, transposed]
-// [QT: running sums of the leaves, transposed][QB: 32 block starts + total].  Leaf e of
-// the 2^D leaves belongs to lane e / PER (PER = 2^D / 32) and sits at (e % PER) * 33 +
-// e / PER: the scouts' per-lane runs and the main warp's two 32-way look-ups are all
-// free of shared-memory bank conflicts (a plain [lane][i] layout costs 32-way conflicts).
+// One staged subtree: [the 2^(D+1) nodes below a level-12 node, relative heap order: node r
+// has children 2r, 2r+1, leaves at r >= 2^D][QB: exclusive running sums of the 32 nodes five
+// levels down + their total].  The nodes arrive by cp.async.bulk (one copy per level, the
+// level's slice is contiguous in the heap): the copy engine goes global -> shared without
+// touching the SM's L1TEX pipe, which the main warp's shared-memory loads depend on (LDG
+// staging with 32 KB in flight behind a 13 KB L1 made every LDS of the SM wait: ncu showed
+// 330-cycle shared loads).
 __host__ __device__ constexpr size_t v6_buf_doubles(int D)
 {
-    return (size_t(1) << D) + 2 * ((size_t(1) << D) / 32) * 33 + 40;
+    return (size_t(2) << D) + 40;
 }
 
 template <int D>
@@ -1198,8 +1209,40 @@ __host__ __device__ constexpr size_t exact_v6_smem_bytes()
 {
     // etop, M, P_lo, P_hi(64) + rootA + stat(2) + pad, sub_own, NBUF x staged buffer, o_prio
     return sizeof(double) * ((size_t(1) << V6_T) + 2 * V6_NTOP + 80 + (size_t(2) << D) +
-                             V6_NBUF * v6_buf_doubles(D) + EX_RING) +
-           sizeof(int) * (EX_RING + 3 * V6_Q + 32) + sizeof(unsigned short) * V6_NTOP + 16;
+                             V6_NBUF * v6_buf_doubles(D) + 2 * EX_RING) +
+           sizeof(int) * 32 + sizeof(unsigned short) * V6_NTOP + 16 + 8 * V6_NBUF;
+}
+
+// One speculative round of R levels on approximate `pos` (see spec_round): the lane whose
+// comparisons are all consistent wins; `safe` is kept only if every comparison of that lane
+// is farther than eps from equality.
+template <int R>
+__device__ __forceinline__ void spec_round_margin(const double *val, int &node, double &pos,
+                                                  bool &safe, double eps, int lane)
+{
+    if constexpr (R > 0) {
+        const int li = lane & ((1 << R) - 1);
+        double left[R];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const int nj = (node << j) + (li >> (R - j));
+            left[j] = val[2 * nj];
+        }
+        double x = pos;
+        bool ok = true, far = true;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const bool right = (li >> (R - 1 - j)) & 1;
+            const double d = x - left[j];
+            ok = ok && ((d < 0.0) != right);
+            far = far && (fabs(d) > eps);
+            x = right ? d : x;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok && far);
+        if constexpr (R < 5) m &= (1u << (1 << R)) - 1u;
+        safe = safe && m != 0;
+        node = (node << R) + (m ? __ffs(m) - 1 : 0);
+    }
 }
 
 template <int D, bool FMA>
@@ -1210,14 +1253,11 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
     constexpr int NTOP = V6_NTOP;
     constexpr int SUBN = 2 << D;
     constexpr int NLEAF = 1 << D;               // leaves under one level-12 node
-    constexpr int PER = NLEAF / 32;             // consecutive leaves owned by one lane
-    constexpr int TR = PER * 33;                // size of a transposed leaf array
     constexpr int BUFN = (int)v6_buf_doubles(D);
-    constexpr int O_LT = NLEAF, O_QT = NLEAF + TR, O_QB = NLEAF + 2 * TR;
+    constexpr int O_QB = SUBN;                  // [33] running sums of the depth-5 nodes
+    constexpr int R2 = D - 5;                   // levels below the 32-way split
     constexpr int PAIRS = (1 << D) - 1;         // child pairs of a whole subtree (slow path)
     constexpr int NIT = (PAIRS + 31) / 32;
-    constexpr int IPAIRS = NLEAF / 2 - 1;       // child pairs above the leaf level
-    constexpr int INIT = (IPAIRS + 31) / 32;
     constexpr int CHUNK = 32;
     constexpr int NSCOUT = V6_NSCOUT, LAG = V6_LAG, NBUF = V6_NBUF, RING = EX_RING;
     constexpr int Q = V6_Q;
@@ -1239,16 +1279,18 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
     unsigned long long *ready64 = reinterpret_cast<unsigned long long *>(s_misc + 8);
     double *sub_own = s_misc + 16;
     double *sub_pref = sub_own + SUBN;          // [NBUF][BUFN]
-    double *o_prio = sub_pref + NBUF * BUFN;    // [RING]
-    int *o_slot = reinterpret_cast<int *>(o_prio + RING); // [RING]
-    int *q_node = o_slot + RING;                // [Q] ascent queue
-    int *q_rel = q_node + Q;
-    int *q_buf = q_rel + Q;
-    int *flags = q_buf + Q;                     // [32]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(flags + 32);
+    // one 16-byte entry per decided draw, read by the ascent warp and by the publisher:
+    // {ring slot of the leaf, staged buffer (NBUF = sub_own), priority}
+    struct DrawEnt {
+        int slot, buf;
+        double prio;
+    };
+    DrawEnt *ring = reinterpret_cast<DrawEnt *>(sub_pref + NBUF * BUFN); // [RING]
+    int *flags = reinterpret_cast<int *>(ring + RING);                   // [32]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(flags + 32); // [1 + NBUF]: top copy, staged buffers
     // 1 + index of the last draw of this launch that chose node o (0 = none): the conflict
     // test "did a draw still in flight touch this subtree" is one load, no vote
-    unsigned short *lastd = reinterpret_cast<unsigned short *>(bar + 2);
+    unsigned short *lastd = reinterpret_cast<unsigned short *>(bar + 2 + NBUF);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 
@@ -1259,6 +1301,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
         flags[F_ASCR] = 0;
         flags[F_PUB] = 0;
         mbar_init(bar, 1);
+        for (int i = 0; i < NBUF; i++) mbar_init(bar + 2 + i, 1);
         mbar_fence_init();
         asm volatile("fence.proxy.async;" ::: "memory");
         mbar_expect_tx(bar, TOPN * 8);
@@ -1311,14 +1354,14 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
         const double pbar = root0 / (double)(a.st->napp - npop); // expected mass per draw
         long long c_wait = 0, c_fetch = 0, c_rest = 0;
         for (int k = warp >> 2; k < a.n; k += NSCOUT) {
-            const long long tc0 = clock64();
+            const long long tc0 = V6_CLK();
             const double uk = a.u[k];
             const int b = k % NBUF;
             int m;
             while ((m = ld_acquire_smem(&flags[F_MAIN])) < k - LAG ||
                    ld_acquire_smem(&flags[F_ASCR]) < k - NBUF + 1)
                 __nanosleep(32 * slp);
-            const long long tc1 = clock64();
+            const long long tc1 = V6_CLK();
             // ---- prediction (any error only costs a slow draw): search the tables
             double pos = uk * (s_misc[0] - (double)(k - m) * pbar);
             int blk = __popc(__ballot_sync(0xffffffffu, pos >= phi[lane])) +
@@ -1332,58 +1375,29 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
             const unsigned unode = (unsigned)(NTOP + (ord ^ oflip));
             const int seen = ld_acquire_smem(&flags[F_ASC]);
             double *dst = sub_pref + b * BUFN;
-            // internal levels: pair q = children of relative node q (q < NLEAF / 2), coalesced
-            double2 ipair[INIT];
+            // ---- one bulk copy per level: the 2^j nodes j levels below `unode` are contiguous
+            uint64_t *sb = bar + 2 + b;
+            if (lane == 0) {
+                mbar_expect_tx(sb, (uint32_t)((SUBN - 2) * 8));
 #pragma unroll
-            for (int it = 0; it < INIT; it++) {
-                int q = lane + 32 * it;
-                q = q < 1 ? 1 : (q > IPAIRS ? IPAIRS : q);
-                const int dq = 31 - __clz(q);
-                ipair[it] = ld_tree_pair(sum2 + ((unode << dq) + (unsigned)(q - (1 << dq))), pol);
+                for (int j = 1; j <= D; j++)
+                    bulk_g2s(dst + (1 << j), a.sum + ((size_t)unode << j), (uint32_t)(8u << j), sb);
             }
-            // leaves: this lane's PER consecutive ones (PER / 2 pairs, PER = 1: half a pair)
-            constexpr int LP = PER >= 2 ? PER / 2 : 1;
-            double2 lpair[LP];
-            const double2 *leaf2 = sum2 + ((size_t)unode << (D - 1)); // pair p = leaves 2p, 2p+1
-#pragma unroll
-            for (int j = 0; j < LP; j++)
-                lpair[j] = ld_tree_pair(leaf2 + (PER >= 2 ? lane * LP + j : lane / 2), pol);
-#pragma unroll
-            for (int it = 0; it < INIT; it++) {
-                int q = lane + 32 * it;
-                q = q < 1 ? 1 : (q > IPAIRS ? IPAIRS : q);
-                reinterpret_cast<double2 *>(dst)[q] = ipair[it];
+            const long long tc2 = V6_CLK();
+            while (!mbar_try_wait(sb, (uint32_t)((k / NBUF) & 1))) {
             }
-            // running sums: start of this lane's block = exclusive scan of the block totals
-            const long long tc2 = clock64();
-            double lf[PER];
-            if constexpr (PER >= 2) {
+            // ---- running sums of the 32 nodes five levels down (warp scan)
+            {
+                const double bs = dst[32 + lane];
+                double incl = bs;
 #pragma unroll
-                for (int j = 0; j < LP; j++) {
-                    lf[2 * j] = lpair[j].x;
-                    lf[2 * j + 1] = lpair[j].y;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
                 }
-            } else {
-                lf[0] = (lane & 1) ? lpair[0].y : lpair[0].x;
+                dst[O_QB + lane] = incl - bs;
+                if (lane == 31) dst[O_QB + 32] = incl;
             }
-            double bs = 0.0;
-#pragma unroll
-            for (int i = 0; i < PER; i++) bs += lf[i];
-            double incl = bs;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
-            }
-            double run = incl - bs;
-            dst[O_QB + lane] = run;
-#pragma unroll
-            for (int i = 0; i < PER; i++) {
-                dst[O_LT + i * 33 + lane] = lf[i];
-                dst[O_QT + i * 33 + lane] = run;
-                run += lf[i];
-            }
-            if (lane == 31) dst[O_QB + 32] = run;
             __syncwarp();
             if (lane == 0) {
                 const unsigned long long wv = ((unsigned long long)(unsigned)k << 32) |
@@ -1394,7 +1408,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                              : "memory");
             }
             __syncwarp();
-            const long long tc3 = clock64();
+            const long long tc3 = V6_CLK();
             c_wait += tc1 - tc0;
             c_fetch += tc2 - tc1;   // prediction + issue of the loads + store of the internal levels
             c_rest += tc3 - tc2;    // leaf loads arrive, running sums, stores, release
@@ -1431,8 +1445,11 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
         long long c_ready = 0, c_decide = 0, c_queue = 0, c_loads = 0, c_stores = 0;
         auto prefetch = [&](int k) {
             const int b = k % NBUF;
+            // plain (volatile) load of the ready word: an acquire would park this warp until
+            // the load returns; the loads below are performed after it in the SM's in-order
+            // shared-memory pipe, behind the scout's release, which is all the ordering needed
             unsigned long long wv;
-            asm volatile("ld.acquire.cta.shared.b64 %0, [%1];"
+            asm volatile("ld.volatile.shared.b64 %0, [%1];"
                          : "=l"(wv)
                          : "r"(smem_u32(&ready64[b]))
                          : "memory");
@@ -1451,7 +1468,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
             while (ld_acquire_smem(&flags[F_PUB]) < k0 + CHUNK - RING) __nanosleep(32);
             for (int kk = 0; kk < kend; kk++) {
                 const int k = k0 + kk;
-                const long long tm0 = clock64();
+                const long long tm0 = V6_CLK();
                 const double uk = __shfl_sync(0xffffffffu, u_lane, kk);
                 const int b = k % NBUF;
                 int ord = 0, rel = 1;
@@ -1479,7 +1496,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                     prefetch(k + 1);
                     pf_stale = true;
                 }
-                const long long tm1 = clock64();
+                const long long tm1 = V6_CLK();
                 if (c_rs == k && !(a.dbg_slow_every > 0 && k % a.dbg_slow_every == 0)) {
                     const int o = c_o;
                     // a draw not yet applied to the exact tree when the copy was taken chose
@@ -1494,25 +1511,20 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                     const double mass = (c_stale && ord_prev == o) ? c_mass - p_prev : c_mass;
                     const double *sub = sub_pref + b * BUFN;
                     bool safe = !conflict && pos > eps && pos < mass - eps;
-                    // two 32-way compares against the running sums of the leaves
+                    // 32-way compare against the running sums of the nodes five levels down,
+                    // then ONE speculative round over the remaining levels
                     int blk = __popc(__ballot_sync(0xffffffffu, pos >= c_qb)) - 1;
                     blk = blk < 0 ? 0 : blk;
-                    int w = 0;
-                    if constexpr (PER > 1) {
-                        const unsigned c2 = __ballot_sync(
-                            0xffffffffu, pos >= sub[O_QT + (lane & (PER - 1)) * 33 + blk]);
-                        w = __popc(c2 & ((1u << PER) - 1u)) - 1;
-                        w = w < 0 ? 0 : w;
-                    }
-                    const double lo = sub[O_QT + w * 33 + blk];
-                    const double hi = (w + 1 < PER) ? sub[O_QT + (w + 1) * 33 + blk]
-                                                    : sub[O_QB + blk + 1];
-                    const double pr = sub[O_LT + w * 33 + blk];
-                    safe = safe && (pos - lo > eps) && (hi - pos > eps);
+                    const double lo = sub[O_QB + blk], hi = sub[O_QB + blk + 1];
+                    double x = pos - lo;
+                    safe = safe && (x > eps) && (hi - pos > eps);
+                    int r = 32 + blk;
+                    spec_round_margin<R2>(sub, r, x, safe, eps, lane);
+                    const double pr = sub[r];
                     if (safe) {
                         fast = true;
                         ord = o;
-                        rel = NLEAF + PER * blk + w;
+                        rel = r;
                         prio = pr;
                         nfast++;
                     }
@@ -1522,6 +1534,13 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                     // ---- slow path: the reference's arithmetic on the exact tree
                     nslow++;
                     while (ld_acquire_smem(&flags[F_ASC]) < k) {
+                    }
+                    // the ascent warp keeps level 12 exact; levels 11..0 = fl(left + right)
+                    for (int lv = T - 2; lv >= 0; lv--) {
+                        const int wdt = 1 << lv;
+                        for (int i = lane; i < wdt; i += 32)
+                            etop[wdt + i] = __dadd_rn(etop[2 * (wdt + i)], etop[2 * (wdt + i) + 1]);
+                        __syncwarp();
                     }
                     double pos = __dmul_rn(etop[1], uk); // np.random.uniform(0.0, root), :302
                     node = older;
@@ -1550,12 +1569,12 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                 } else {
                     node = NTOP + (ord ^ oflip);
                 }
-                const long long tm2 = clock64();
+                const long long tm2 = V6_CLK();
                 // room in the ascent queue: Q entries, checked every fourth draw
                 if ((k & 3) == 0)
                     while (ld_acquire_smem(&flags[F_ASCR]) < k - Q + 4) {
                     }
-                const long long tm3 = clock64();
+                const long long tm3 = V6_CLK();
                 rootA = rootA - prio;
                 // ---- loads first: this draw's table entries
                 const int base = ord & ~63, within = ord & 63, bk = ord >> 6;
@@ -1563,17 +1582,17 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                 const double t_l0 = plo[base + lane], t_l1 = plo[base + lane + 32];
                 const double t_h0 = phi[lane], t_h1 = phi[lane + 32];
                 // ---- then the stores: ascent queue, publisher ring, approximate tables
-                const long long tm4 = clock64();
+                const long long tm4 = V6_CLK();
                 if (lane == 0) {
-                    q_node[k % Q] = node;
-                    q_rel[k % Q] = rel;
-                    q_buf[k % Q] = fast ? b : NBUF;
-                    lastd[ord] = (unsigned short)(k + 1);
                     const unsigned leafnode = ((unsigned)node << D) + (unsigned)(rel - (1 << D));
-                    o_slot[k % RING] = (int)(leafnode - (unsigned)a.nslots);
-                    o_prio[k % RING] = prio;
+                    DrawEnt e;
+                    e.slot = (int)(leafnode - (unsigned)a.nslots);
+                    e.buf = fast ? b : NBUF;
+                    e.prio = prio;
+                    *reinterpret_cast<int4 *>(&ring[k % RING]) = *reinterpret_cast<int4 *>(&e);
+                    lastd[ord] = (unsigned short)(k + 1);
                     mtab[ord] = t_m - prio;
-                    s_misc[0] = rootA;
+                    if ((k & 3) == 3) s_misc[0] = rootA; // the scouts' estimate tolerates the lag
                 }
                 if (lane > within) plo[base + lane] = t_l0 - prio;
                 if (lane + 32 > within) plo[base + lane + 32] = t_l1 - prio;
@@ -1589,7 +1608,7 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                     asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(smem_u32(&flags[F_MAIN])),
                                  "r"(k + 1)
                                  : "memory");
-                const long long tm5 = clock64();
+                const long long tm5 = V6_CLK();
                 c_ready += tm1 - tm0;
                 c_decide += tm2 - tm1;
                 c_queue += tm3 - tm2;
@@ -1609,24 +1628,24 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
         // --------------- ascent: _write(ix, 0.0) on the exact tree ---------------
         long long c_await = 0, c_awork = 0;
         for (int k = 0; k < a.n; k++) {
-            const long long ta0 = clock64();
+            const long long ta0 = V6_CLK();
             while (ld_acquire_smem(&flags[F_MAIN]) <= k) __nanosleep(20 * slp);
-            const long long ta1 = clock64();
-            const int node = q_node[k % Q];
-            const int rel = q_rel[k % Q];
-            const int bid = q_buf[k % Q];
+            const long long ta1 = V6_CLK();
+            const int4 ev = *reinterpret_cast<const int4 *>(&ring[k % RING]);
+            const unsigned lfn = (unsigned)a.nslots + (unsigned)ev.x; // heap index of the leaf
+            const int node = (int)(lfn >> D);
+            const int rel = NLEAF + (int)(lfn & (NLEAF - 1));
+            const int bid = ev.y;
             const double *sub = bid < NBUF ? sub_pref + bid * BUFN : sub_own;
             const unsigned unode = (unsigned)node;
-            double sib[D + T - 1];
-            {
-                // the sibling leaf: transposed array of a staged buffer, plain layout of sub_own
-                const int e = (rel - NLEAF) ^ 1;
-                sib[0] = bid < NBUF ? sub[O_LT + (e % PER) * 33 + e / PER] : sub[rel ^ 1];
-            }
+            // Only the D levels below the shared-memory top are re-reduced per draw.  Every
+            // node above is fl(left + right) of its children at all times, so levels 11..0 of
+            // the exact top are a pure function of level 12: they are recomputed once when
+            // the batch ends (and before a slow-path draw needs them) -- half the chain,
+            // half the instructions of the warp that bounds the pipeline.
+            double sib[D];
 #pragma unroll
-            for (int j = 1; j < D; j++) sib[j] = sub[(rel >> j) ^ 1];
-#pragma unroll
-            for (int j = 0; j < T - 1; j++) sib[D + j] = etop[(node >> j) ^ 1];
+            for (int j = 0; j < D; j++) sib[j] = sub[(rel >> j) ^ 1];
             const unsigned leafnode = (unode << D) + (unsigned)(rel - (1 << D));
             double v = 0.0;
             if (lane == 0) st_tree(a.sum + leafnode, 0.0, pol);
@@ -1640,11 +1659,6 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                         etop[node] = v;
                 }
             }
-#pragma unroll
-            for (int j = 0; j < T - 1; j++) {
-                v = __dadd_rn(v, sib[D + j]);
-                if (lane == 0) etop[node >> (j + 1)] = v;
-            }
             __syncwarp();
             if (lane == 0) {
                 // inputs consumed: a plain store ordered after the loads that fed the chain
@@ -1652,12 +1666,15 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
                 // visibility of the global stores: every ASC_BATCH draws, and whenever
                 // the main warp has nothing more queued (it may be waiting for us)
                 if ((k + 1) % ASC_BATCH == 0 || k + 1 == a.n ||
-                    *reinterpret_cast<volatile int *>(&flags[F_MAIN]) == k + 1)
+                    *reinterpret_cast<volatile int *>(&flags[F_MAIN]) == k + 1) {
+                    // the scouts read the bottom levels with the bulk-copy engine (async proxy)
+                    asm volatile("fence.proxy.async;" ::: "memory");
                     st_release_smem(&flags[F_ASC], k + 1);
+                }
             }
             __syncwarp();
             c_await += ta1 - ta0;
-            c_awork += clock64() - ta1;
+            c_awork += V6_CLK() - ta1;
         }
         if (a.dbg_cycles && lane == 0) {
             a.dbg_cycles[16] = c_await;
@@ -1676,8 +1693,8 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
             }
             const int k = k0 + lane;
             if (k < kend) {
-                const long long slot = o_slot[k % RING];
-                const double prio = o_prio[k % RING];
+                const long long slot = ring[k % RING].slot;
+                const double prio = ring[k % RING].prio;
                 a.slots_out[k] = (int32_t)slot;
                 a.prio_out[k] = prio;
                 if (a.index_out) a.index_out[k] = (slot - npop) & mask;
@@ -1702,6 +1719,13 @@ __device__ __forceinline__ void exact_deep_v6(const SampleArgs &a, double *smem_
         }
     }
     __syncthreads();
+    // levels 11..0 of the exact top from level 12 (see the ascent warp)
+    for (int lv = T - 2; lv >= 0; lv--) {
+        const int wdt = 1 << lv;
+        for (int i = threadIdx.x; i < wdt; i += blockDim.x)
+            etop[wdt + i] = __dadd_rn(etop[2 * (wdt + i)], etop[2 * (wdt + i) + 1]);
+        __syncthreads();
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) {
