@@ -230,7 +230,7 @@ RAINBOW_UPDATE_INTERVAL = 4
 def make_rainbow_agent(buf, dev_index, batch, grad_sync=None, cuda_graph=False):
     import torch
     from pfrl_b200 import agents, explorers, nn as pnn, parallel, q_functions
-    from pfrl_b200.utils.phi import ScaleU8
+    from pfrl_b200.utils.phi import RawU8
 
     torch.manual_seed(0)
     q = q_functions.DistributionalDuelingDQN(18, 51, -10, 10)
@@ -240,7 +240,7 @@ def make_rainbow_agent(buf, dev_index, batch, grad_sync=None, cuda_graph=False):
     agent = agents.CategoricalDoubleDQN(
         q, opt, buf, gpu=dev_index, gamma=GAMMA, explorer=explorers.Greedy(),
         minibatch_size=batch, replay_start_size=batch, target_update_interval=32000,
-        update_interval=RAINBOW_UPDATE_INTERVAL, batch_accumulator="mean", phi=ScaleU8(),
+        update_interval=RAINBOW_UPDATE_INTERVAL, batch_accumulator="mean", phi=RawU8(),
         grad_sync=grad_sync, cuda_graph=cuda_graph)
     parallel.broadcast_parameters(agent.model)
     parallel.broadcast_parameters(agent.target_model)
@@ -707,6 +707,8 @@ def main():
             "updates": res["value"][1], "update_interval": RAINBOW_UPDATE_INTERVAL,
             "ms_per_update_incl_acting": tml[3] / max(res["value"][1], 1),
             "minibatch_per_rank": B, "dtype": "fp32 (TF32 off)", "cuda_graph": graph,
+            "observations": "uint8 minibatches out of the replay gather; x / 255 applied inside "
+                            "conv1 (b2rl_conv_nature1_fwd_u8), same numbers as f32 batches",
             "model": "DistributionalDuelingDQN(18, 51) + factorized noisy, Adam(6.25e-5)",
             "note": "value: GPU-resident synthetic env; e2e: host numpy env (frames H2D, "
                     "actions D2H); gradient all-reduce (NCCL) when n_gpus > 1"}

@@ -399,6 +399,60 @@ int b2rl_conv_nature1_fwd_u8(const uint8_t *x, float scale, const float *w,
                              const float *bias, int32_t n_images, float *out,
                              void *stream);
 
+/* ------------------------------------------------------------------------
+ * Dense layers on the tcgen05 tensor cores with fp32 results (3 x TF32 split):
+ *   C[M,N] = A[M,K] . B[N,K]^T (+ bias[N]) (relu)
+ * Replaces the cuBLAS SGEMM behind F.linear and its two backward products
+ * (pfrl/q_functions/dueling_dqn.py:67-129, pfrl/nn/noisy_linear.py:53-70,
+ * pfrl/nn/atari_cnn.py:17-47).  a_mn_major / b_mn_major = 0: the operand is stored
+ * row-major with the contraction index contiguous ([M][K] / [N][K], leading dimension
+ * lda / ldb); = 1: stored with the contraction index as the row index ([K][M] / [K][N]),
+ * which is how dX = dY . W (B = W) and dW = dY^T . X (A = dY, B = X) read their operands
+ * without a transposed copy.  Small products are cut along K; the partial tiles need
+ * b2rl_gemm_workspace_bytes(M, N, K) bytes of 16-byte aligned device memory (0 = none)
+ * and are summed in a fixed order, so results are run-to-run deterministic.
+ * bias may be NULL. */
+int64_t b2rl_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int b2rl_gemm_tf32x3(const float *A, int32_t lda, int32_t a_mn_major,
+                     const float *B, int32_t ldb, int32_t b_mn_major,
+                     const float *bias, int32_t relu, float *C, int32_t ldc,
+                     int32_t M, int32_t N, int32_t K,
+                     void *workspace, int64_t workspace_bytes, void *stream);
+
+/* The same product with operands that are read in place through index tables: the
+ * convolutions of the Nature trunk (pfrl/nn/atari_cnn.py:30-44,
+ * pfrl/q_functions/dueling_dqn.py:34-40,91-97 -- cuDNN forward / dgrad / wgrad in the
+ * reference) as implicit GEMMs.  A gather operand's element (row, k) lives at
+ *   row_tab[2 row] + k_tab[2 k] + ((y + dy) >> shift) * pitch + ((x + dx) >> shift)
+ * with y | x << 16 = row_tab[2 row + 1] (unsigned 16-bit halves) and dy | dx << 16 =
+ * k_tab[2 k + 1] (signed 16-bit halves), and is zero unless 0 <= y + dy < y_limit,
+ * 0 <= x + dx < x_limit and both sums are multiples of 1 << shift.  uint8 sources are
+ * read as float(byte) * scale.  The output is dense (ld) or, with row_tab, scattered:
+ * C[m, n] at row_tab[m] + n * col_stride.  pfrl_b200/ops/conv.py builds the tables. */
+enum { B2RL_GEMM_K_MAJOR = 0, B2RL_GEMM_MN_MAJOR = 1, B2RL_GEMM_GATHER = 2 };
+typedef struct b2rl_gemm_operand {
+    const void *data;        /* fp32, or uint8 when u8 != 0 (gather mode only) */
+    int32_t mode;            /* B2RL_GEMM_* */
+    int32_t ld;              /* dense modes: elements between rows */
+    const int32_t *row_tab;  /* gather: 2 ints per row (device memory, 8-byte aligned) */
+    const int32_t *k_tab;    /* gather: 2 ints per k */
+    int32_t y_limit, x_limit, shift, pitch;
+    int32_t lanes_along_k;   /* coalescing hint: consecutive k are close in memory */
+    int32_t u8;
+    float scale;
+} b2rl_gemm_operand;
+typedef struct b2rl_gemm_output {
+    float *data;
+    int32_t ld;              /* dense: C[m * ld + n] */
+    const int32_t *row_tab;  /* scatter when not NULL */
+    int32_t col_stride;
+    const float *bias;       /* [N] or NULL */
+    int32_t relu;
+} b2rl_gemm_output;
+int b2rl_gemm_tf32x3_ex(const b2rl_gemm_operand *A, const b2rl_gemm_operand *B,
+                        const b2rl_gemm_output *C, int32_t M, int32_t N, int32_t K,
+                        void *workspace, int64_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

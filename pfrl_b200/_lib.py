@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libb2rl.so")
-SOURCES = ["replay.cu", "sampler.cu", "step.cu", "gather.cu", "losses.cu", "ppo.cu", "sac.cu", "conv.cu"]
+SOURCES = ["replay.cu", "sampler.cu", "step.cu", "gather.cu", "losses.cu", "ppo.cu", "sac.cu", "conv.cu", "gemm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -113,6 +113,23 @@ class StepArgs(ctypes.Structure):
     ]
 
 
+class GemmOperand(ctypes.Structure):
+    """b2rl_gemm_operand (include/b2rl.h)."""
+    _fields_ = [("data", ctypes.c_void_p), ("mode", ctypes.c_int32), ("ld", ctypes.c_int32),
+                ("row_tab", ctypes.c_void_p), ("k_tab", ctypes.c_void_p),
+                ("y_limit", ctypes.c_int32), ("x_limit", ctypes.c_int32),
+                ("shift", ctypes.c_int32), ("pitch", ctypes.c_int32),
+                ("lanes_along_k", ctypes.c_int32), ("u8", ctypes.c_int32),
+                ("scale", ctypes.c_float)]
+
+
+class GemmOutput(ctypes.Structure):
+    """b2rl_gemm_output (include/b2rl.h)."""
+    _fields_ = [("data", ctypes.c_void_p), ("ld", ctypes.c_int32),
+                ("row_tab", ctypes.c_void_p), ("col_stride", ctypes.c_int32),
+                ("bias", ctypes.c_void_p), ("relu", ctypes.c_int32)]
+
+
 class TensorPair(ctypes.Structure):
     _fields_ = [("dst", ctypes.c_void_p), ("src", ctypes.c_void_p), ("numel", ctypes.c_int64)]
 
@@ -174,6 +191,11 @@ SIGNATURES = {
     "b2rl_sac_target": (_int, [_vp] * 7 + [ctypes.c_float, _i32, _vp, _vp]),
     "b2rl_conv_nature1_fwd": (_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
     "b2rl_conv_nature1_fwd_u8": (_int, [_vp, ctypes.c_float, _vp, _vp, _i32, _vp, _vp]),
+    "b2rl_gemm_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "b2rl_gemm_tf32x3": (_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
+                                _i32, _i32, _i32, _vp, _i64, _vp]),
+    "b2rl_gemm_tf32x3_ex": (_int, [ctypes.POINTER(GemmOperand), ctypes.POINTER(GemmOperand),
+                                   ctypes.POINTER(GemmOutput), _i32, _i32, _i32, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -1,10 +1,11 @@
-"""Atari convolutional trunks (pfrl/nn/atari_cnn.py:17-82).  Plain PyTorch:
-these dense contractions are the only tensor-core work on the path and are
-served by cuDNN / cuBLAS."""
+"""Atari convolutional trunks (pfrl/nn/atari_cnn.py:17-82).  The first convolution and the
+fully connected head have their own kernels (nn/fast_conv.py: exact-fp32 direct convolution;
+ops/linear.py: tcgen05 3xTF32 product); the middle convolutions are cuDNN's."""
 import torch.nn as nn
 import torch.nn.functional as F
 
 from pfrl_b200.nn.fast_conv import NatureConv1
+from pfrl_b200.ops.linear import TCLinear
 from pfrl_b200.initializers import constant_bias_initializer, init_chainer_default
 
 
@@ -14,7 +15,7 @@ class _AtariCNN(nn.Module):
         self.activation = activation
         self.n_output_channels = n_output_channels
         self.layers = nn.ModuleList(convs)
-        self.output = nn.Linear(flat, n_output_channels)
+        self.output = TCLinear(flat, n_output_channels)
         self.apply(init_chainer_default)
         self.apply(constant_bias_initializer(bias=bias))
 

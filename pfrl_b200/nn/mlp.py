@@ -13,7 +13,8 @@ class MLP(nn.Module):
     the reference so that state_dicts are interchangeable.
     """
 
-    def __init__(self, in_size, out_size, hidden_sizes, nonlinearity=F.relu, last_wscale=1):
+    def __init__(self, in_size, out_size, hidden_sizes, nonlinearity=F.relu, last_wscale=1,
+                 linear_cls=nn.Linear):
         super().__init__()
         self.in_size, self.out_size = in_size, out_size
         self.hidden_sizes = hidden_sizes
@@ -25,10 +26,10 @@ class MLP(nn.Module):
             # layer after that: the reference's order, so that the same torch seed gives
             # the same initial weights (tests/test_checkpoint_interchange_cpu.py)
             self.hidden_layers = nn.ModuleList(
-                [nn.Linear(a, b) for a, b in zip(widths, widths[1:])])
+                [linear_cls(a, b) for a, b in zip(widths, widths[1:])])
             for layer in self.hidden_layers:
                 init_chainer_default(layer)
-        self.output = nn.Linear(widths[-1], out_size)
+        self.output = linear_cls(widths[-1], out_size)
         init_lecun_normal(self.output.weight, scale=last_wscale)
         nn.init.zeros_(self.output.bias)
 

@@ -5,6 +5,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from pfrl_b200.ops.linear import linear as _linear
+
 
 @torch.no_grad()
 def _lecun_uniform_(w, scale):
@@ -52,5 +54,6 @@ class FactorizedNoisyLinear(nn.Module):
         eps_in, eps_out = eps[:n_in], eps[n_in:]
         weight = torch.addcmul(self.mu.weight, sw, torch.outer(eps_out, eps_in))
         if not self.hasbias:
-            return F.linear(x, weight)
-        return F.linear(x, weight, torch.addcmul(self.mu.bias, self.sigma.bias, eps_out))
+            return _linear(x, weight)
+        # CUDA: tcgen05 product with fp32 results (csrc/gemm.cu); elsewhere F.linear
+        return _linear(x, weight, torch.addcmul(self.mu.bias, self.sigma.bias, eps_out))

@@ -9,6 +9,7 @@ from pfrl_b200 import action_value
 from pfrl_b200.initializers import constant_bias_initializer, init_chainer_default
 from pfrl_b200.nn.fast_conv import NatureConv1
 from pfrl_b200.nn.mlp import MLP
+from pfrl_b200.ops.linear import TCLinear
 from pfrl_b200.q_function import StateQFunction
 
 
@@ -29,8 +30,8 @@ class DuelingDQN(nn.Module, StateQFunction):
         self.activation = activation
         super().__init__()
         self.conv_layers = _nature_convs(n_input_channels)
-        self.a_stream = MLP(3136, n_actions, [512])
-        self.v_stream = MLP(3136, 1, [512])
+        self.a_stream = MLP(3136, n_actions, [512], linear_cls=TCLinear)
+        self.v_stream = MLP(3136, 1, [512], linear_cls=TCLinear)
         self.conv_layers.apply(init_chainer_default)
         self.conv_layers.apply(constant_bias_initializer(bias=bias))
 
@@ -60,9 +61,10 @@ class DistributionalDuelingDQN(nn.Module, StateQFunction):
         super().__init__()
         self.z_values = torch.linspace(v_min, v_max, n_atoms, dtype=torch.float32)
         self.conv_layers = _nature_convs(n_input_channels)
-        self.main_stream = nn.Linear(3136, 1024)
-        self.a_stream = nn.Linear(512, n_actions * n_atoms)
-        self.v_stream = nn.Linear(512, n_atoms)
+        # TCLinear IS an nn.Linear; on CUDA its products run on the tensor cores (ops/linear.py)
+        self.main_stream = TCLinear(3136, 1024)
+        self.a_stream = TCLinear(512, n_actions * n_atoms)
+        self.v_stream = TCLinear(512, n_atoms)
         self.apply(init_chainer_default)
         self.conv_layers.apply(constant_bias_initializer(bias=bias))
 
