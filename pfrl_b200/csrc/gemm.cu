@@ -18,9 +18,10 @@
 // Data movement: no TMA tensor maps.  The split has to touch every element anyway, so sixteen
 // loader warps read the fp32 tiles through the read-only path, split them in registers and
 // store hi and lo straight into the canonical no-swizzle K-major core-matrix layout the tensor
-// core reads (8 rows x 16 B per core matrix; a quarter warp writes one 128-byte core matrix:
-// conflict free).  Operands whose contraction index is the contiguous one ("K-major": X and W
-// in the forward product) are read with 16-byte loads, 8 rows x 64 B per warp instruction;
+// core reads (8 rows x 16 B per core matrix, K-neighbours padded to 144 B so that every
+// quarter warp stores to 8 different bank groups).  Operands whose contraction index is the
+// contiguous one ("K-major": X and W in the forward product) are read with 16-byte loads, four
+// whole 128-byte rows per warp instruction;
 // operands whose contraction index is the ROW index ("MN-major": dY and X in dW = dY^T . X,
 // W in dX = dY . W) are read with four 4-byte loads per thread, each warp instruction one
 // coalesced 128-byte run along M/N, and the four k values meet in one 16-byte store -- the
@@ -61,7 +62,12 @@ constexpr int EPI_WARPS = 4;
 constexpr int MMA_WARP = 4;
 constexpr int LOAD_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 1 + LOAD_WARPS) * 32; // 672
-constexpr int TILE_BYTES = BM * BK * 4;                    // 16 KB
+// Shared-memory tile of one operand half (hi or lo): 16 row groups x 8 k chunks of 8 x 16 B core
+// matrices.  The cores that are neighbours along K sit 144 bytes apart (128 + 16 of padding),
+// so that the 8 lanes which hold one row's eight k chunks store to 8 different bank groups.
+constexpr int CORE_K_BYTES = 144;                          // "leading" byte offset
+constexpr int CORE_MN_BYTES = 8 * CORE_K_BYTES;            // "stride" byte offset (8-row groups)
+constexpr int TILE_BYTES = (BM / 8) * CORE_MN_BYTES;       // 18 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;                // A_hi A_lo B_hi B_lo
 constexpr int TMEM_COLS = 256; // two 128-column accumulators: hi.hi and the correction terms
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
@@ -197,12 +203,10 @@ __device__ __forceinline__ float4 load4(const float *p, bool row_ok, int n_valid
 }
 
 // One operand tile of one stage: 128 (M or N) x 32 (K) floats, stored K-major: core matrix
-// (rg, kc) = rows 8 rg .. 8 rg + 7, k 4 kc .. 4 kc + 3, at (rg * 8 + kc) * 128 bytes.  Each
-// loader thread owns two 16-byte vectors (4 consecutive k of one row) per operand and stage,
-// in one of two lane arrangements:
-//   along k   : unit u = 8 rows x 16 k; lanes 4r .. 4r+3 hold row r (one 64-byte run per row,
-//               8 L1 wavefronts per instruction); the vectors are exchanged between lanes at
-//               store time so that every quarter warp stores one whole core matrix.
+// (rg, kc) = rows 8 rg .. 8 rg + 7, k 4 kc .. 4 kc + 3.  Each loader thread owns two 16-byte
+// vectors (4 consecutive k of one row) per operand and stage, in one of two lane arrangements:
+//   along k   : unit u = rows 4u .. 4u+3 x all 32 k; lanes 8r .. 8r+7 hold row r (a whole
+//               128-byte row per 8 lanes: 4 L1 wavefronts per 16-byte load instruction).
 //   along rows: unit u = 32 rows x 4 k; lane = row (each warp load instruction is one coalesced
 //               run along M/N); the four k values of a thread meet in its 16-byte store -- this
 //               is the transposition of the MN-major operands.
@@ -210,28 +214,44 @@ struct Frag {
     float4 v[2];
 };
 
-struct RowInfo { // per thread and operand, fixed for the whole tile
-    int row[2];      // tile-relative row of unit 0 / 1 (>= rows_valid: nothing to load)
-    int2 tab[2];     // gather: row table entries
+template <int MODE> struct Lane { // per thread and operand, fixed for the whole tile
+    const float *q[2]; // dense modes: address of this thread's element of k block 0
+    int2 tab[2];       // gather: row table entries
+    int kofs[2];       // k offset of the thread's vector inside a k block
+    int soff[2];       // byte offset of its 16-byte slot inside a tile half, -1: nothing to do
+    bool along_k;
 };
 
-__device__ __forceinline__ bool lanes_along_k(const Operand &o)
+template <int MODE>
+__device__ __forceinline__ void lane_setup(const Operand &o, int mn0, int mn_total, int tile_rows,
+                                           int k_first, int lw, int lane, Lane<MODE> &L)
 {
-    return o.mode == MODE_K_MAJOR || (o.mode == MODE_GATHER && o.along_k);
-}
-
-__device__ __forceinline__ void row_info(const Operand &o, int mn0, int mn_total, int tile_rows,
-                                         int lw, int lane, RowInfo &ri)
-{
-    const bool ak = lanes_along_k(o);
+    L.along_k = MODE == MODE_K_MAJOR || (MODE == MODE_GATHER && o.along_k);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const int u = lw + 16 * i;
-        const int r = ak ? (u >> 1) * 8 + (lane >> 2) : (u & 3) * 32 + lane;
+        const int u = lw + 16 * i; // 32 units per tile
+        int r, kc;
+        if (L.along_k) {
+            r = 4 * u + (lane >> 3), kc = lane & 7;
+        } else {
+            r = (u & 3) * 32 + lane, kc = u >> 2;
+        }
+        L.kofs[i] = kc * 4;
+        // rows past the N tile are never read by the tensor core; rows past the matrix are zero
+        L.soff[i] = r < tile_rows ? (r >> 3) * CORE_MN_BYTES + kc * CORE_K_BYTES + (r & 7) * 16
+                                  : -1;
         const bool ok = r < tile_rows && mn0 + r < mn_total;
-        ri.row[i] = ok ? r : -1;
-        ri.tab[i] = make_int2(0, 0);
-        if (ok && o.mode == MODE_GATHER) ri.tab[i] = __ldg(o.row_tab + mn0 + r);
+        L.q[i] = nullptr;
+        L.tab[i] = make_int2(0, 0);
+        if (!ok) continue;
+        if (MODE == MODE_K_MAJOR)
+            L.q[i] = (const float *)o.p + (size_t)(mn0 + r) * o.ld + k_first + kc * 4;
+        else if (MODE == MODE_MN_MAJOR)
+            L.q[i] = (const float *)o.p + (size_t)(k_first + kc * 4) * o.ld + mn0 + r;
+        else {
+            L.q[i] = (const float *)o.p; // (marks the row as present)
+            L.tab[i] = __ldg(o.row_tab + mn0 + r);
+        }
     }
 }
 
@@ -250,70 +270,58 @@ __device__ __forceinline__ float gather1(const Operand &o, int2 rt, int k, int k
     return __ldg((const float *)o.p + idx);
 }
 
-__device__ __forceinline__ void fetch_operand(const Operand &o, const RowInfo &ri, int mn0,
-                                              int k0, int k_total, int lw, int lane, Frag &f)
+// k block `kb` (relative to the first one of this CTA) -> registers.  `full`: the whole block
+// lies inside K (warp-uniform), which is the common case and needs no per-element checks.
+template <int MODE>
+__device__ __forceinline__ void fetch_operand(const Operand &o, const Lane<MODE> &L, int kb,
+                                              int k0, int k_total, Frag &f)
 {
-    const bool ak = lanes_along_k(o);
+    const bool full = k0 + BK <= k_total;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const int u = lw + 16 * i; // 32 units per tile
         f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ri.row[i] < 0) continue;
-        const int kk = ak ? k0 + ((u & 1) * 4 + (lane & 3)) * 4 : k0 + (u >> 2) * 4;
-        if (o.mode == MODE_K_MAJOR) {
-            const float *q = (const float *)o.p + (size_t)(mn0 + ri.row[i]) * o.ld + kk;
-            f.v[i] = load4(q, true, k_total - kk, o.vec);
-        } else if (o.mode == MODE_MN_MAJOR) {
-            const float *q = (const float *)o.p + (size_t)kk * o.ld + mn0 + ri.row[i];
-            if (kk < k_total) f.v[i].x = __ldg(q);
-            if (kk + 1 < k_total) f.v[i].y = __ldg(q + o.ld);
-            if (kk + 2 < k_total) f.v[i].z = __ldg(q + 2 * (size_t)o.ld);
-            if (kk + 3 < k_total) f.v[i].w = __ldg(q + 3 * (size_t)o.ld);
+        if (L.q[i] == nullptr) continue;
+        if (MODE == MODE_K_MAJOR) {
+            const float *q = L.q[i] + (size_t)kb * BK;
+            if (full && o.vec)
+                f.v[i] = __ldg(reinterpret_cast<const float4 *>(q));
+            else
+                f.v[i] = load4(q, true, k_total - (k0 + L.kofs[i]), o.vec);
+        } else if (MODE == MODE_MN_MAJOR) {
+            const float *q = L.q[i] + (size_t)kb * BK * o.ld;
+            const int left = k_total - (k0 + L.kofs[i]);
+            if (full || left > 0) f.v[i].x = __ldg(q);
+            if (full || left > 1) f.v[i].y = __ldg(q + o.ld);
+            if (full || left > 2) f.v[i].z = __ldg(q + 2 * (size_t)o.ld);
+            if (full || left > 3) f.v[i].w = __ldg(q + 3 * (size_t)o.ld);
         } else {
-            f.v[i].x = gather1(o, ri.tab[i], kk, k_total);
-            f.v[i].y = gather1(o, ri.tab[i], kk + 1, k_total);
-            f.v[i].z = gather1(o, ri.tab[i], kk + 2, k_total);
-            f.v[i].w = gather1(o, ri.tab[i], kk + 3, k_total);
+            const int kk = k0 + L.kofs[i];
+            f.v[i].x = gather1(o, L.tab[i], kk, k_total);
+            f.v[i].y = gather1(o, L.tab[i], kk + 1, k_total);
+            f.v[i].z = gather1(o, L.tab[i], kk + 2, k_total);
+            f.v[i].w = gather1(o, L.tab[i], kk + 3, k_total);
         }
     }
 }
 
-// tile_rows < 128 (narrow N tiles): the units that lie entirely outside are skipped (uniformly
-// per warp), the tensor core never reads those rows.
-__device__ __forceinline__ void store_operand(const Operand &o, const Frag &f, int tile_rows,
-                                              uint8_t *s_hi, uint8_t *s_lo, int lw, int lane)
+template <int MODE>
+__device__ __forceinline__ void store_operand(const Lane<MODE> &L, const Frag &f, uint8_t *s_hi,
+                                              uint8_t *s_lo)
 {
-    const bool ak = lanes_along_k(o);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const int u = lw + 16 * i;
-        int off;
-        if (ak) {
-            if ((u >> 1) * 8 >= tile_rows) continue;
-            off = ((u >> 1) * 8 + (u & 1) * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
-        } else {
-            if ((u & 3) * 32 >= tile_rows) continue;
-            const int r = (u & 3) * 32 + lane;
-            off = ((r >> 3) * 8 + (u >> 2)) * 128 + (r & 7) * 16;
-        }
-        float4 t = f.v[i];
-        if (ak) { // loaded as lane = 4 row + vector, stored as lane = 8 vector + row
-            const int src = (lane & 7) * 4 + (lane >> 3);
-            t.x = __shfl_sync(0xffffffffu, t.x, src);
-            t.y = __shfl_sync(0xffffffffu, t.y, src);
-            t.z = __shfl_sync(0xffffffffu, t.z, src);
-            t.w = __shfl_sync(0xffffffffu, t.w, src);
-        }
+        if (L.soff[i] < 0) continue;
         uint4 h, l;
-        split_tf32(t.x, h.x, l.x);
-        split_tf32(t.y, h.y, l.y);
-        split_tf32(t.z, h.z, l.z);
-        split_tf32(t.w, h.w, l.w);
-        *reinterpret_cast<uint4 *>(s_hi + off) = h;
-        *reinterpret_cast<uint4 *>(s_lo + off) = l;
+        split_tf32(f.v[i].x, h.x, l.x);
+        split_tf32(f.v[i].y, h.y, l.y);
+        split_tf32(f.v[i].z, h.z, l.z);
+        split_tf32(f.v[i].w, h.w, l.w);
+        *reinterpret_cast<uint4 *>(s_hi + L.soff[i]) = h;
+        *reinterpret_cast<uint4 *>(s_lo + L.soff[i]) = l;
     }
 }
 
+template <int AMODE, int BMODE>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constant__ GemmArgs g)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -356,26 +364,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
     if (warp > MMA_WARP) {
         // ---------------- loaders ----------------
         const int lw = warp - MMA_WARP - 1;
-        RowInfo ra, rb;
-        row_info(g.A, m0, g.M, BM, lw, lane, ra);
-        row_info(g.B, n0, g.N, g.bn, lw, lane, rb);
+        Lane<AMODE> la;
+        Lane<BMODE> lb;
+        lane_setup<AMODE>(g.A, m0, g.M, BM, kb0 * BK, lw, lane, la);
+        lane_setup<BMODE>(g.B, n0, g.N, g.bn, kb0 * BK, lw, lane, lb);
         Frag fa, fb;
-        fetch_operand(g.A, ra, m0, kb0 * BK, g.K, lw, lane, fa);
-        fetch_operand(g.B, rb, n0, kb0 * BK, g.K, lw, lane, fb);
+        fetch_operand<AMODE>(g.A, la, 0, kb0 * BK, g.K, fa);
+        fetch_operand<BMODE>(g.B, lb, 0, kb0 * BK, g.K, fb);
         for (int it = 0; it < n_kb; it++) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             Frag na = fa, nb = fb; // next k block: in flight while this one is split and stored
             if (it + 1 < n_kb) {
                 const int k1 = (kb0 + it + 1) * BK;
-                fetch_operand(g.A, ra, m0, k1, g.K, lw, lane, na);
-                fetch_operand(g.B, rb, n0, k1, g.K, lw, lane, nb);
+                fetch_operand<AMODE>(g.A, la, it + 1, k1, g.K, na);
+                fetch_operand<BMODE>(g.B, lb, it + 1, k1, g.K, nb);
             }
             if (lane == 0) mbar_wait(empty0 + 8 * s, ph ^ 1);
             __syncwarp();
             uint8_t *st = smem + s * STAGE_BYTES;
-            store_operand(g.A, fa, BM, st, st + TILE_BYTES, lw, lane);
-            store_operand(g.B, fb, g.bn, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, lw, lane);
+            store_operand<AMODE>(la, fa, st, st + TILE_BYTES);
+            store_operand<BMODE>(lb, fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
             // generic-proxy stores -> visible to the tensor core (async proxy)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -389,9 +398,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
             // (both operands K-major in shared memory: the loaders transpose)
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
                                    ((uint32_t)(g.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            // neighbours along K: 128 B; 8-row groups: 1024 B; one k step = two k chunks
-            const uint32_t a_lead = 128u, a_stride = 1024u, b_lead = 128u, b_stride = 1024u;
-            const uint32_t a_step = 256u, b_step = 256u;
+            // neighbours along K: 144 B; 8-row groups: 1152 B; one k step = two k chunks
+            const uint32_t a_lead = CORE_K_BYTES, a_stride = CORE_MN_BYTES;
+            const uint32_t b_lead = CORE_K_BYTES, b_stride = CORE_MN_BYTES;
+            const uint32_t a_step = 2 * CORE_K_BYTES, b_step = 2 * CORE_K_BYTES;
             for (int it = 0; it < n_kb; it++) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -604,16 +614,22 @@ extern "C" int b2rl_gemm_tf32x3_ex(const b2rl_gemm_operand *A, const b2rl_gemm_o
                      (long long)need);
         g.partial = (float *)workspace;
     }
-    static bool attr_set[64]; // per device
+    typedef void (*kernel_t)(GemmArgs);
+    static const kernel_t kernels[3][3] = {
+        {k_gemm_tf32x3<0, 0>, k_gemm_tf32x3<0, 1>, k_gemm_tf32x3<0, 2>},
+        {k_gemm_tf32x3<1, 0>, k_gemm_tf32x3<1, 1>, k_gemm_tf32x3<1, 2>},
+        {k_gemm_tf32x3<2, 0>, k_gemm_tf32x3<2, 1>, k_gemm_tf32x3<2, 2>}};
+    const kernel_t kernel = kernels[g.A.mode][g.B.mode];
+    static bool attr_set[64][3][3]; // per device and instantiation
     int cur_dev = 0;
     B2RL_CUDA(cudaGetDevice(&cur_dev));
-    if (cur_dev < 0 || cur_dev >= 64 || !attr_set[cur_dev]) {
-        B2RL_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cur_dev < 0 || cur_dev >= 64 || !attr_set[cur_dev][g.A.mode][g.B.mode]) {
+        B2RL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SMEM_BYTES));
-        if (cur_dev >= 0 && cur_dev < 64) attr_set[cur_dev] = true;
+        if (cur_dev >= 0 && cur_dev < 64) attr_set[cur_dev][g.A.mode][g.B.mode] = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + g.bn - 1) / g.bn);
-    k_gemm_tf32x3<<<tiles * g.splits, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(g);
+    kernel<<<tiles * g.splits, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(g);
     B2RL_CUDA(cudaGetLastError());
     if (g.splits > 1) {
         const long long total = (long long)M * N;

@@ -1,10 +1,12 @@
 """Atari convolutional trunks (pfrl/nn/atari_cnn.py:17-82).  The first convolution and the
 fully connected head have their own kernels (nn/fast_conv.py: exact-fp32 direct convolution;
-ops/linear.py: tcgen05 3xTF32 product); the middle convolutions are cuDNN's."""
+ops/linear.py: tcgen05 3xTF32 product); the other convolutions run as implicit GEMMs on the
+tensor cores (ops/conv.py), forward and backward."""
 import torch.nn as nn
 import torch.nn.functional as F
 
 from pfrl_b200.nn.fast_conv import NatureConv1
+from pfrl_b200.ops.conv import TCConv2d
 from pfrl_b200.ops.linear import TCLinear
 from pfrl_b200.initializers import constant_bias_initializer, init_chainer_default
 
@@ -32,8 +34,8 @@ class LargeAtariCNN(_AtariCNN):
     def __init__(self, n_input_channels=4, n_output_channels=512, activation=F.relu, bias=0.1):
         self.n_input_channels = n_input_channels
         super().__init__(
-            [NatureConv1(n_input_channels), nn.Conv2d(32, 64, 4, stride=2),
-             nn.Conv2d(64, 64, 3, stride=1)], 3136, n_output_channels, activation, bias)
+            [NatureConv1(n_input_channels), TCConv2d(32, 64, 4, stride=2),
+             TCConv2d(64, 64, 3, stride=1)], 3136, n_output_channels, activation, bias)
 
 
 class SmallAtariCNN(_AtariCNN):
@@ -42,5 +44,5 @@ class SmallAtariCNN(_AtariCNN):
     def __init__(self, n_input_channels=4, n_output_channels=256, activation=F.relu, bias=0.1):
         self.n_input_channels = n_input_channels
         super().__init__(
-            [nn.Conv2d(n_input_channels, 16, 8, stride=4), nn.Conv2d(16, 32, 4, stride=2)],
+            [TCConv2d(n_input_channels, 16, 8, stride=4), TCConv2d(16, 32, 4, stride=2)],
             2592, n_output_channels, activation, bias)

@@ -4,8 +4,8 @@
 same state_dict keys).  On CUDA, for contiguous fp32 [N, 4, 84, 84] inputs
 that do not require grad (observations), the forward runs
 ``b2rl_conv_nature1_fwd`` (csrc/conv.cu: exact fp32 FFMA accumulation, several
-times faster than cuDNN's TF32-off path); weight / bias gradients come from
-``aten::convolution_backward``.  uint8 inputs (phi = utils.phi.RawU8: the replay gather
+times faster than cuDNN's TF32-off path); the weight gradient is a tensor-core implicit GEMM
+(ops/conv.py, read straight from the bytes for uint8 inputs).  uint8 inputs (phi = utils.phi.RawU8: the replay gather
 emits bytes) go through ``b2rl_conv_nature1_fwd_u8``, which applies ``x * input_scale``
 while it stages the image, so the f32 batch is never written to HBM.  Everything else
 falls through to cuDNN.
@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from pfrl_b200 import _lib
+from pfrl_b200.ops import conv as conv_ops
 
 
 class _Conv1Fn(torch.autograd.Function):
@@ -38,6 +39,10 @@ class _Conv1Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
+        if conv_ops.enabled() and x.shape[0] >= 8:
+            gw = conv_ops.geometry(x.shape[0], 4, 84, 84, 32, 8, 8, 4, str(x.device)) \
+                .wgrad(x, grad_out)
+            return None, gw, grad_out.sum((0, 2, 3)) if ctx.has_bias else None
         _, gw, gb = torch.ops.aten.convolution_backward(
             grad_out.contiguous(), x, weight, [32] if ctx.has_bias else None, [4, 4], [0, 0],
             [1, 1], False, [0, 0], 1, [False, True, ctx.has_bias])
@@ -68,6 +73,11 @@ class _Conv1U8Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
+        if conv_ops.enabled() and x.shape[0] >= 8:
+            # tensor-core weight gradient straight from the bytes (ops/conv.py)
+            gw = conv_ops.geometry(x.shape[0], 4, 84, 84, 32, 8, 8, 4, str(x.device)) \
+                .wgrad(x, grad_out, scale=ctx.scale)
+            return None, gw, grad_out.sum((0, 2, 3)) if ctx.has_bias else None, None
         xf = x.to(torch.float32) * ctx.scale
         _, gw, gb = torch.ops.aten.convolution_backward(
             grad_out.contiguous(), xf, weight, [32] if ctx.has_bias else None, [4, 4], [0, 0],

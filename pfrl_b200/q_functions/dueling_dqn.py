@@ -9,6 +9,7 @@ from pfrl_b200 import action_value
 from pfrl_b200.initializers import constant_bias_initializer, init_chainer_default
 from pfrl_b200.nn.fast_conv import NatureConv1
 from pfrl_b200.nn.mlp import MLP
+from pfrl_b200.ops.conv import TCConv2d
 from pfrl_b200.ops.linear import TCLinear
 from pfrl_b200.q_function import StateQFunction
 
@@ -16,8 +17,8 @@ from pfrl_b200.q_function import StateQFunction
 def _nature_convs(n_input_channels):
     return nn.ModuleList([
         NatureConv1(n_input_channels),
-        nn.Conv2d(32, 64, 4, stride=2),
-        nn.Conv2d(64, 64, 3, stride=1),
+        TCConv2d(32, 64, 4, stride=2),  # nn.Conv2d run as implicit GEMMs on the tensor cores
+        TCConv2d(64, 64, 3, stride=1),
     ])
 
 
