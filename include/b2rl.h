@@ -423,20 +423,24 @@ int b2rl_gemm_tf32x3(const float *A, int32_t lda, int32_t a_mn_major,
  * convolutions of the Nature trunk (pfrl/nn/atari_cnn.py:30-44,
  * pfrl/q_functions/dueling_dqn.py:34-40,91-97 -- cuDNN forward / dgrad / wgrad in the
  * reference) as implicit GEMMs.  A gather operand's element (row, k) lives at
- *   row_tab[2 row] + k_tab[2 k] + ((y + dy) >> shift) * pitch + ((x + dx) >> shift)
- * with y | x << 16 = row_tab[2 row + 1] (unsigned 16-bit halves) and dy | dx << 16 =
- * k_tab[2 k + 1] (signed 16-bit halves), and is zero unless 0 <= y + dy < y_limit,
- * 0 <= x + dx < x_limit and both sums are multiples of 1 << shift.  uint8 sources are
- * read as float(byte) * scale.  The output is dense (ld) or, with row_tab, scattered:
- * C[m, n] at row_tab[m] + n * col_stride.  pfrl_b200/ops/conv.py builds the tables. */
+ *   row_off[row] + k_off[k]
+ * and -- when the coordinate tables are given -- is zero unless
+ *   0 <= y + dy < y_limit and 0 <= x + dx < x_limit,
+ * y | x << 16 = row_yx[row] (unsigned 16-bit halves), dy | dx << 16 = k_yx[k] (signed 16-bit
+ * halves).  The k tables must be padded to a multiple of 32 entries and 16-byte aligned.
+ * uint8 sources are read as float(byte) * scale.  The output is dense (ld) or, with
+ * row_tab, scattered: C[m, n] at row_tab[m] + n * col_stride.  pfrl_b200/ops/conv.py builds
+ * the tables (forward, input gradient per stride phase, weight gradient). */
 enum { B2RL_GEMM_K_MAJOR = 0, B2RL_GEMM_MN_MAJOR = 1, B2RL_GEMM_GATHER = 2 };
 typedef struct b2rl_gemm_operand {
     const void *data;        /* fp32, or uint8 when u8 != 0 (gather mode only) */
     int32_t mode;            /* B2RL_GEMM_* */
     int32_t ld;              /* dense modes: elements between rows */
-    const int32_t *row_tab;  /* gather: 2 ints per row (device memory, 8-byte aligned) */
-    const int32_t *k_tab;    /* gather: 2 ints per k */
-    int32_t y_limit, x_limit, shift, pitch;
+    const int32_t *row_off;  /* gather: element offset per row (device memory) */
+    const int32_t *row_yx;   /* gather: coordinates per row, or NULL */
+    const int32_t *k_off;    /* gather: element offset per k */
+    const int32_t *k_yx;     /* gather: coordinate steps per k, or NULL */
+    int32_t y_limit, x_limit;
     int32_t lanes_along_k;   /* coalescing hint: consecutive k are close in memory */
     int32_t u8;
     float scale;
@@ -449,6 +453,9 @@ typedef struct b2rl_gemm_output {
     const float *bias;       /* [N] or NULL */
     int32_t relu;
 } b2rl_gemm_output;
+/* Debug aid: %globaltimer stamps of the phases of every CTA of the following launches are
+ * written to device_buffer (8 x uint64 per CTA); NULL switches it off. */
+int b2rl_gemm_debug_times(void *device_buffer);
 int b2rl_gemm_tf32x3_ex(const b2rl_gemm_operand *A, const b2rl_gemm_operand *B,
                         const b2rl_gemm_output *C, int32_t M, int32_t N, int32_t K,
                         void *workspace, int64_t workspace_bytes, void *stream);

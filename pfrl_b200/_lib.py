@@ -116,9 +116,9 @@ class StepArgs(ctypes.Structure):
 class GemmOperand(ctypes.Structure):
     """b2rl_gemm_operand (include/b2rl.h)."""
     _fields_ = [("data", ctypes.c_void_p), ("mode", ctypes.c_int32), ("ld", ctypes.c_int32),
-                ("row_tab", ctypes.c_void_p), ("k_tab", ctypes.c_void_p),
+                ("row_off", ctypes.c_void_p), ("row_yx", ctypes.c_void_p),
+                ("k_off", ctypes.c_void_p), ("k_yx", ctypes.c_void_p),
                 ("y_limit", ctypes.c_int32), ("x_limit", ctypes.c_int32),
-                ("shift", ctypes.c_int32), ("pitch", ctypes.c_int32),
                 ("lanes_along_k", ctypes.c_int32), ("u8", ctypes.c_int32),
                 ("scale", ctypes.c_float)]
 
@@ -194,6 +194,7 @@ SIGNATURES = {
     "b2rl_gemm_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "b2rl_gemm_tf32x3": (_int, [_vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                                 _i32, _i32, _i32, _vp, _i64, _vp]),
+    "b2rl_gemm_debug_times": (_int, [_vp]),
     "b2rl_gemm_tf32x3_ex": (_int, [ctypes.POINTER(GemmOperand), ctypes.POINTER(GemmOperand),
                                    ctypes.POINTER(GemmOutput), _i32, _i32, _i32, _vp, _i64, _vp]),
 }

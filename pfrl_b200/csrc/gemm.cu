@@ -27,16 +27,16 @@
 // coalesced 128-byte run along M/N, and the four k values meet in one 16-byte store -- the
 // transposition happens in registers, no transposed copy is ever made and the tensor core only
 // ever sees K-major tiles (kind::tf32 accepts MN-major tiles only in a 32-bit swizzled layout).
-// The loads of k block i+1 are issued before block i is split and stored, so the global-load
-// latency hides behind the conversion.
+// The loads of k blocks i+1 and i+2 are in flight while block i is split and stored, so the
+// global-load latency hides behind the conversion.
 //
-// Roles in a CTA of 21 warps, one 128 x 128 output tile (x one K split) per CTA:
-//   warps 0-3   epilogue: tcgen05.ld the two accumulators (TMEM lane = tile row), add, bias /
-//               relu, store
-//   warp  4     allocates 256 TMEM columns; lane 0 issues 3 MMAs per 8-wide k step (hi.hi into
+// Roles in a CTA of 17 warps, one 128 x 128 output tile (x one K split) per CTA:
+//   warp  0     allocates 256 TMEM columns; lane 0 issues 3 MMAs per 8-wide k step (hi.hi into
 //               one accumulator, lo.hi + hi.lo into the other)
-//   warps 5-20  loaders, 3-stage ring of (A_hi, A_lo, B_hi, B_lo) = 64 KB per stage,
+//   warps 1-16  loaders, 3-stage ring of (A_hi, A_lo, B_hi, B_lo) = 72 KB per stage,
 //               full/empty mbarriers; the empty side is armed by tcgen05.commit
+//   warps 1-16  then the epilogue: tcgen05.ld the two accumulators (TMEM lane = tile row), add,
+//               bias / relu, store (four warps per TMEM lane quarter, interleaved column chunks)
 // Small products are split along K so that the grid covers the 148 SMs; the partial tiles go
 // to a workspace and `k_gemm_reduce` adds them in a fixed order (deterministic), with the
 // bias / relu epilogue.
@@ -44,13 +44,14 @@
 // Convolutions (pfrl/nn/atari_cnn.py:30-44, pfrl/q_functions/dueling_dqn.py:34-40,91-97: the
 // 4x4/2 and 3x3/1 layers of the Nature trunk, forward, input gradient, weight gradient) are the
 // same product with one more operand mode, "gather": element (row, k) lives at
-//   row_off[row] + k_off[k] + ((y[row] + dy[k]) >> shift) * pitch + ((x[row] + dx[k]) >> shift)
-// and exists iff 0 <= y + dy < y_limit, 0 <= x + dx < x_limit and both are multiples of
-// 1 << shift -- im2col, its transpose (col2im as a gather, strided layers included) and the
-// pixel-major views of the weight gradient, all read in place through two small index tables
-// per operand (ops/conv.py builds them once per layer shape).  The output can be scattered the
-// same way (C[m, n] at row_off[m] + n * col_stride: NCHW activations and transposed weight
-// gradients), so no im2col buffer and no layout pass ever touches HBM.  uint8 sources
+//   row_off[row] + k_off[k]
+// and, when the operand carries coordinates, exists iff 0 <= y[row] + dy[k] < y_limit and
+// 0 <= x[row] + dx[k] < x_limit -- im2col, its transpose (col2im as a gather; a strided layer
+// is one product per stride phase) and the pixel-major views of the weight gradient, all read
+// in place through small int32 tables per operand (ops/conv.py builds them once per layer
+// shape).  The output can be scattered the same way (C[m, n] at row_off[m] + n * col_stride:
+// NCHW activations and transposed weight gradients), so no im2col buffer and no layout pass
+// ever touches HBM.  uint8 sources
 // (float(byte) * scale: the x / 255 of the Atari phi) are read directly.
 #include "b2rl_internal.cuh"
 
@@ -58,10 +59,9 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32; // BK floats = 128 bytes of contraction per stage
 constexpr int STAGES = 3;
-constexpr int EPI_WARPS = 4;
-constexpr int MMA_WARP = 4;
+constexpr int MMA_WARP = 0;
 constexpr int LOAD_WARPS = 16;
-constexpr int THREADS = (EPI_WARPS + 1 + LOAD_WARPS) * 32; // 672
+constexpr int THREADS = (1 + LOAD_WARPS) * 32; // 544
 // Shared-memory tile of one operand half (hi or lo): 16 row groups x 8 k chunks of 8 x 16 B core
 // matrices.  The cores that are neighbours along K sit 144 bytes apart (128 + 16 of padding),
 // so that the 8 lanes which hold one row's eight k chunks store to 8 different bank groups.
@@ -79,10 +79,10 @@ struct Operand {
     const void *p; // float, or uint8_t when u8
     int mode;
     int ld, vec;   // dense modes: leading dimension, 16-byte loads allowed
-    // gather mode (see the header comment)
-    const int2 *row_tab; // (element offset, y | x << 16)
-    const int2 *k_tab;   // (element offset, dy | dx << 16), int16 each
-    int y_limit, x_limit, shift, pitch;
+    // gather mode (see the header comment); k tables are padded to a multiple of 32 entries
+    const int *row_off, *row_yx; // element offset; y | x << 16 (NULL: no coordinates)
+    const int *k_off, *k_yx;     // element offset; dy | dx << 16, int16 each
+    int y_limit, x_limit;
     int along_k;         // consecutive lanes walk k (else rows)
     int u8;
     float scale;
@@ -100,7 +100,17 @@ struct GemmArgs {
     int bn;              // N tile: 32, 64 or 128
     int splits, kb_per_split;
     int relu;
+    unsigned long long *times; // debug (B2RL_GEMM_TIMES): 8 %globaltimer stamps per CTA, or NULL
 };
+
+__device__ __forceinline__ void stamp(const GemmArgs &g, int slot)
+{
+    if (g.times) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g.times[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -118,19 +128,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
                  : "memory");
 }
 
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{ .reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return done != 0;
+}
+
+// try_wait suspends the thread in hardware for a while by itself; the clock is read only every
+// 256 polls, to turn a lost arrival into a trap instead of a hang.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+    if (mbar_try(bar, parity)) return;
     const long long t0 = clock64();
-    for (;;) {
-        uint32_t done;
-        asm volatile("{ .reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done)
-                     : "r"(bar), "r"(parity)
-                     : "memory");
-        if (done) return;
-        if (clock64() - t0 > WAIT_LIMIT) __trap();
+    for (uint32_t spins = 1;; spins++) {
+        if (mbar_try(bar, parity)) return;
+        if ((spins & 255u) == 0 && clock64() - t0 > WAIT_LIMIT) __trap();
     }
 }
 
@@ -216,7 +234,8 @@ struct Frag {
 
 template <int MODE> struct Lane { // per thread and operand, fixed for the whole tile
     const float *q[2]; // dense modes: address of this thread's element of k block 0
-    int2 tab[2];       // gather: row table entries
+    int roff[2], ryx[2]; // gather: row table entries
+    int tko[3], tkc[3];  // gather: k table entries of three k blocks in flight, lane = k mod 32
     int kofs[2];       // k offset of the thread's vector inside a k block
     int soff[2];       // byte offset of its 16-byte slot inside a tile half, -1: nothing to do
     bool along_k;
@@ -242,7 +261,7 @@ __device__ __forceinline__ void lane_setup(const Operand &o, int mn0, int mn_tot
                                   : -1;
         const bool ok = r < tile_rows && mn0 + r < mn_total;
         L.q[i] = nullptr;
-        L.tab[i] = make_int2(0, 0);
+        L.roff[i] = L.ryx[i] = 0;
         if (!ok) continue;
         if (MODE == MODE_K_MAJOR)
             L.q[i] = (const float *)o.p + (size_t)(mn0 + r) * o.ld + k_first + kc * 4;
@@ -250,35 +269,81 @@ __device__ __forceinline__ void lane_setup(const Operand &o, int mn0, int mn_tot
             L.q[i] = (const float *)o.p + (size_t)(k_first + kc * 4) * o.ld + mn0 + r;
         else {
             L.q[i] = (const float *)o.p; // (marks the row as present)
-            L.tab[i] = __ldg(o.row_tab + mn0 + r);
+            L.roff[i] = __ldg(o.row_off + mn0 + r);
+            if (o.row_yx) L.ryx[i] = __ldg(o.row_yx + mn0 + r);
         }
     }
 }
 
-__device__ __forceinline__ float gather1(const Operand &o, int2 rt, int k, int k_total)
+__device__ __forceinline__ float gather_load(const Operand &o, int idx)
 {
-    if (k >= k_total) return 0.f;
-    const int2 kt = __ldg(o.k_tab + k);
-    const int yy = (int)(short)(rt.y & 0xffff) + (int)(short)(kt.y & 0xffff);
-    const int xx = (rt.y >> 16) + (kt.y >> 16);
-    const int mask = (1 << o.shift) - 1;
-    if ((unsigned)yy >= (unsigned)o.y_limit || (unsigned)xx >= (unsigned)o.x_limit ||
-        ((yy | xx) & mask))
-        return 0.f;
-    const int idx = rt.x + kt.x + (yy >> o.shift) * o.pitch + (xx >> o.shift);
     if (o.u8) return (float)__ldg((const uint8_t *)o.p + idx) * o.scale;
     return __ldg((const float *)o.p + idx);
+}
+
+// k table entries of one k block -> one register per lane (coalesced; the tables are padded to
+// a multiple of 32).  Issued one iteration before the data loads that need them, so that the
+// gather is not a chain of two dependent global loads.
+template <int MODE>
+__device__ __forceinline__ void table_fetch(const Operand &o, Lane<MODE> &L, int slot, int k0,
+                                            int lane)
+{
+    if (MODE != MODE_GATHER) return;
+    L.tko[slot] = __ldg(o.k_off + k0 + lane);
+    L.tkc[slot] = o.k_yx ? __ldg(o.k_yx + k0 + lane) : 0;
+}
+
+// Four consecutive k (block-relative kofs .. kofs + 3) of one row; `n` = how many of them lie
+// inside K.  All lanes take part in the shuffles, `present` says whether this lane has a row.
+__device__ __forceinline__ float4 gather4(const Operand &o, bool present, int roff, int ryx,
+                                          int tko, int tkc, int kofs, int n)
+{
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 ko;
+    ko.x = __shfl_sync(0xffffffffu, tko, kofs);
+    ko.y = __shfl_sync(0xffffffffu, tko, kofs + 1);
+    ko.z = __shfl_sync(0xffffffffu, tko, kofs + 2);
+    ko.w = __shfl_sync(0xffffffffu, tko, kofs + 3);
+    if (o.row_yx == nullptr) {
+        if (!present || n <= 0) return v;
+        v.x = gather_load(o, roff + ko.x);
+        if (n > 1) v.y = gather_load(o, roff + ko.y);
+        if (n > 2) v.z = gather_load(o, roff + ko.z);
+        if (n > 3) v.w = gather_load(o, roff + ko.w);
+        return v;
+    }
+    int4 kc;
+    kc.x = __shfl_sync(0xffffffffu, tkc, kofs);
+    kc.y = __shfl_sync(0xffffffffu, tkc, kofs + 1);
+    kc.z = __shfl_sync(0xffffffffu, tkc, kofs + 2);
+    kc.w = __shfl_sync(0xffffffffu, tkc, kofs + 3);
+    if (!present || n <= 0) return v;
+    const int ry = ryx & 0xffff, rx = ryx >> 16;
+    const unsigned yl = (unsigned)o.y_limit, xl = (unsigned)o.x_limit;
+#define B2RL_OK_AT(c) \
+    ((unsigned)(ry + (int)(short)((c) & 0xffff)) < yl && (unsigned)(rx + ((c) >> 16)) < xl)
+    if (B2RL_OK_AT(kc.x)) v.x = gather_load(o, roff + ko.x);
+    if (n > 1 && B2RL_OK_AT(kc.y)) v.y = gather_load(o, roff + ko.y);
+    if (n > 2 && B2RL_OK_AT(kc.z)) v.z = gather_load(o, roff + ko.z);
+    if (n > 3 && B2RL_OK_AT(kc.w)) v.w = gather_load(o, roff + ko.w);
+#undef B2RL_OK_AT
+    return v;
 }
 
 // k block `kb` (relative to the first one of this CTA) -> registers.  `full`: the whole block
 // lies inside K (warp-uniform), which is the common case and needs no per-element checks.
 template <int MODE>
 __device__ __forceinline__ void fetch_operand(const Operand &o, const Lane<MODE> &L, int kb,
-                                              int k0, int k_total, Frag &f)
+                                              int slot, int k0, int k_total, Frag &f)
 {
     const bool full = k0 + BK <= k_total;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
+        if (MODE == MODE_GATHER) {
+            f.v[i] = gather4(o, L.q[i] != nullptr, L.roff[i], L.ryx[i], L.tko[slot], L.tkc[slot],
+                             L.kofs[i], full ? 4 : k_total - (k0 + L.kofs[i]));
+            continue;
+        }
         f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (L.q[i] == nullptr) continue;
         if (MODE == MODE_K_MAJOR) {
@@ -287,19 +352,13 @@ __device__ __forceinline__ void fetch_operand(const Operand &o, const Lane<MODE>
                 f.v[i] = __ldg(reinterpret_cast<const float4 *>(q));
             else
                 f.v[i] = load4(q, true, k_total - (k0 + L.kofs[i]), o.vec);
-        } else if (MODE == MODE_MN_MAJOR) {
+        } else {
             const float *q = L.q[i] + (size_t)kb * BK * o.ld;
             const int left = k_total - (k0 + L.kofs[i]);
             if (full || left > 0) f.v[i].x = __ldg(q);
             if (full || left > 1) f.v[i].y = __ldg(q + o.ld);
             if (full || left > 2) f.v[i].z = __ldg(q + 2 * (size_t)o.ld);
             if (full || left > 3) f.v[i].w = __ldg(q + 3 * (size_t)o.ld);
-        } else {
-            const int kk = k0 + L.kofs[i];
-            f.v[i].x = gather1(o, L.tab[i], kk, k_total);
-            f.v[i].y = gather1(o, L.tab[i], kk + 1, k_total);
-            f.v[i].z = gather1(o, L.tab[i], kk + 2, k_total);
-            f.v[i].w = gather1(o, L.tab[i], kk + 3, k_total);
         }
     }
 }
@@ -341,6 +400,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
     const uint32_t accum_bar = smem_u32(&bars[2 * STAGES]);
 
+    if (threadIdx.x == 0) stamp(g, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full0 + 8 * s, LOAD_WARPS);
@@ -360,6 +420,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
+    if (threadIdx.x == 0) stamp(g, 1); // set-up done (barriers, TMEM)
 
     if (warp > MMA_WARP) {
         // ---------------- loaders ----------------
@@ -368,28 +429,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
         Lane<BMODE> lb;
         lane_setup<AMODE>(g.A, m0, g.M, BM, kb0 * BK, lw, lane, la);
         lane_setup<BMODE>(g.B, n0, g.N, g.bn, kb0 * BK, lw, lane, lb);
-        Frag fa, fb;
-        fetch_operand<AMODE>(g.A, la, 0, kb0 * BK, g.K, fa);
-        fetch_operand<BMODE>(g.B, lb, 0, kb0 * BK, g.K, fb);
-        for (int it = 0; it < n_kb; it++) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            Frag na = fa, nb = fb; // next k block: in flight while this one is split and stored
-            if (it + 1 < n_kb) {
-                const int k1 = (kb0 + it + 1) * BK;
-                fetch_operand<AMODE>(g.A, la, it + 1, k1, g.K, na);
-                fetch_operand<BMODE>(g.B, lb, it + 1, k1, g.K, nb);
+        // Two k blocks are in flight in registers while a third is split and stored: the
+        // global-load latency (DRAM-cold operands: ~1.5 us) is spread over two iterations.
+        // The ring of three register fragments lines up with the three smem stages.
+        static_assert(STAGES == 3, "the loader loop is unrolled over the stage ring");
+        Frag fa[3], fb[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (j < n_kb) {
+                table_fetch<AMODE>(g.A, la, j, (kb0 + j) * BK, lane);
+                table_fetch<BMODE>(g.B, lb, j, (kb0 + j) * BK, lane);
             }
-            if (lane == 0) mbar_wait(empty0 + 8 * s, ph ^ 1);
-            __syncwarp();
-            uint8_t *st = smem + s * STAGE_BYTES;
-            store_operand<AMODE>(la, fa, st, st + TILE_BYTES);
-            store_operand<BMODE>(lb, fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
-            // generic-proxy stores -> visible to the tensor core (async proxy)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);
-            fa = na, fb = nb;
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+            if (j < n_kb) {
+                fetch_operand<AMODE>(g.A, la, j, j, (kb0 + j) * BK, g.K, fa[j]);
+                fetch_operand<BMODE>(g.B, lb, j, j, (kb0 + j) * BK, g.K, fb[j]);
+            }
+        for (int it0 = 0; it0 < n_kb; it0 += 3) {
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const int it = it0 + s;
+                if (it >= n_kb) break;
+                const uint32_t ph = (it / STAGES) & 1;
+                if (it + 2 < n_kb) {
+                    const int k2 = (kb0 + it + 2) * BK;
+                    fetch_operand<AMODE>(g.A, la, it + 2, (s + 2) % 3, k2, g.K, fa[(s + 2) % 3]);
+                    fetch_operand<BMODE>(g.B, lb, it + 2, (s + 2) % 3, k2, g.K, fb[(s + 2) % 3]);
+                }
+                if (it + 3 < n_kb) { // table slot s belonged to block `it`, whose loads are out
+                    table_fetch<AMODE>(g.A, la, s, (kb0 + it + 3) * BK, lane);
+                    table_fetch<BMODE>(g.B, lb, s, (kb0 + it + 3) * BK, lane);
+                }
+                if (lane == 0) mbar_wait(empty0 + 8 * s, ph ^ 1);
+                __syncwarp();
+                uint8_t *st = smem + s * STAGE_BYTES;
+                store_operand<AMODE>(la, fa[s], st, st + TILE_BYTES);
+                store_operand<BMODE>(lb, fb[s], st + 2 * TILE_BYTES, st + 3 * TILE_BYTES);
+                // generic-proxy stores -> visible to the tensor core (async proxy)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + 8 * s);
+            }
         }
     } else if (warp == MMA_WARP) {
         // ---------------- MMA issue: one thread ----------------
@@ -406,6 +487,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(full0 + 8 * s, ph);
+                if (it == 0) stamp(g, 2); // first stage filled
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t sb = sa + 2 * TILE_BYTES;
@@ -425,14 +507,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
                 mma_commit(empty0 + 8 * s); // arrives when the MMAs above have read the stage
             }
             mma_commit(accum_bar);
+            stamp(g, 3); // last MMA issued
         }
         __syncwarp();
-    } else {
-        // ---------------- epilogue: warp w owns TMEM lanes 32w .. 32w+31 ----------------
+    }
+    if (warp >= 1) {
+        // ---------------- epilogue: all sixteen loader warps, once their loads are done.  A
+        // warp may touch the TMEM lanes 32 (warp % 4) .. 32 (warp % 4) + 31; the four warps
+        // that share a quarter take every fourth 16-column chunk each ----------------
+        const int quarter = warp & 3, part = (warp - 1) >> 2;
         if (lane == 0) mbar_wait(accum_bar, 0);
         __syncwarp();
+        if (warp == 1 && lane == 0) stamp(g, 4); // accumulators complete
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + warp * 32 + lane;
+        const int row = m0 + quarter * 32 + lane;
         const bool direct = g.splits == 1;
         const bool scatter = direct && g.c_row_tab != nullptr;
         float *out = direct ? g.C : g.partial + (size_t)split * g.M * g.N;
@@ -442,40 +530,87 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
                                                      : (long long)row * ldo)
                                           : 0;
         const int ostride = scatter ? g.c_col_stride : 1;
+        // Dense outputs go through shared memory (the operand ring is idle by now): a thread
+        // owns a ROW of the accumulator, so storing it directly would write 16-byte pieces of
+        // 32 different rows per instruction (half-empty sectors, 4-byte pieces when C is not
+        // 16-byte aligned).  Staged as [128][bn + 4] floats, the tile leaves in whole rows.
+        // Scattered outputs (NCHW activations) are already coalesced across the lanes.
+        constexpr int SROW = BN + 4;
+        float *stage_tile = reinterpret_cast<float *>(smem);
 #pragma unroll 1
-        for (int c = 0; c < g.bn / 16; c++) {
+        for (int c = part; c < g.bn / 16; c += 4) {
             uint32_t r[16], q[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + c * 16;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + c * 16;
             tmem_ld16(taddr, r);
             tmem_ld16(taddr + BN, q);
             tmem_wait();
             const int col0 = n0 + c * 16;
-            if (row < g.M && col0 < g.N) {
-                float v[16];
+            float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    v[j] = __uint_as_float(r[j]) + __uint_as_float(q[j]);
-                    if (direct && col0 + j < g.N) {
-                        if (g.bias) v[j] += __ldg(g.bias + col0 + j);
-                        if (g.relu) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]) + __uint_as_float(q[j]);
+            if (!scatter) {
+                float *o = stage_tile + (quarter * 32 + lane) * SROW + c * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else if (row < g.M && col0 < g.N) {
+                float *o = out + obase + (long long)col0 * ostride;
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (col0 + j < g.N) {
+                        float x = v[j];
+                        if (g.bias) x += __ldg(g.bias + col0 + j);
+                        if (g.relu) x = fmaxf(x, 0.f);
+                        o[(long long)j * ostride] = x; // lane = row: one run per column
+                    }
+            }
+        }
+        if (!scatter) {
+            asm volatile("bar.sync 1, %0;" ::"n"(LOAD_WARPS * 32) : "memory");
+            const int t = threadIdx.x - 32; // 0 .. 511
+            const bool bias_relu = direct;
+            if (vec && (n0 & 3) == 0) {
+                const int per_row = g.bn / 4;
+                for (int idx = t; idx < BM * per_row; idx += LOAD_WARPS * 32) {
+                    const int rr = idx / per_row, cc = (idx % per_row) * 4;
+                    if (m0 + rr >= g.M || n0 + cc >= g.N) continue;
+                    float4 x = *reinterpret_cast<const float4 *>(stage_tile + rr * SROW + cc);
+                    float *o = out + (size_t)(m0 + rr) * ldo + n0 + cc;
+                    if (n0 + cc + 4 <= g.N) {
+                        if (bias_relu && g.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + cc));
+                            x.x += bv.x, x.y += bv.y, x.z += bv.z, x.w += bv.w;
+                        }
+                        if (bias_relu && g.relu)
+                            x.x = fmaxf(x.x, 0.f), x.y = fmaxf(x.y, 0.f), x.z = fmaxf(x.z, 0.f),
+                            x.w = fmaxf(x.w, 0.f);
+                        *reinterpret_cast<float4 *>(o) = x;
+                    } else {
+                        const float xs[4] = {x.x, x.y, x.z, x.w};
+                        for (int j = 0; j < 4 && n0 + cc + j < g.N; j++) {
+                            float y = xs[j];
+                            if (bias_relu && g.bias) y += __ldg(g.bias + n0 + cc + j);
+                            if (bias_relu && g.relu) y = fmaxf(y, 0.f);
+                            o[j] = y;
+                        }
                     }
                 }
-                float *o = out + obase + (long long)col0 * ostride;
-                if (!scatter && vec && col0 + 16 <= g.N) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4 *>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                    // scatter: lane = row, so for each column the warp writes one run
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (col0 + j < g.N) o[(long long)j * ostride] = v[j];
+            } else {
+                for (int idx = t; idx < BM * g.bn; idx += LOAD_WARPS * 32) {
+                    const int rr = idx / g.bn, cc = idx % g.bn;
+                    if (m0 + rr >= g.M || n0 + cc >= g.N) continue;
+                    float y = stage_tile[rr * SROW + cc];
+                    if (bias_relu && g.bias) y += __ldg(g.bias + n0 + cc);
+                    if (bias_relu && g.relu) y = fmaxf(y, 0.f);
+                    out[(size_t)(m0 + rr) * ldo + n0 + cc] = y;
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (warp == 1 && lane == 0) stamp(g, 5); // epilogue stores issued
     }
     __syncthreads();
+    if (threadIdx.x == 0) stamp(g, 6);
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -484,25 +619,39 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
     }
 }
 
-// C = sum over the K splits (fixed order) + bias, relu; dense or scattered like the epilogue.
+// C = sum over the K splits + bias, relu; dense or scattered like the epilogue.  A block of
+// 8 warps works on 32 consecutive outputs: warp w adds the splits w, w + 8, ... (coalesced
+// 128-byte reads), the eight partial sums meet in shared memory and are added in warp order --
+// the order of the additions never depends on timing, so results are run-to-run identical.
 __global__ void __launch_bounds__(256) k_gemm_reduce(const float *__restrict__ partial, int splits,
                                                      int M, int N, const float *__restrict__ bias,
                                                      int relu, float *__restrict__ C, int ldc,
                                                      const int *__restrict__ row_tab,
                                                      int col_stride)
 {
+    __shared__ float red[8][32];
     const size_t total = (size_t)M * N;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (size_t)gridDim.x * blockDim.x) {
-        float acc = partial[i];
-        for (int s = 1; s < splits; s++) acc += partial[(size_t)s * total + i];
-        const int m = (int)(i / N), n = (int)(i % N);
-        if (bias) acc += __ldg(bias + n);
-        if (relu) acc = fmaxf(acc, 0.f);
-        if (row_tab)
-            C[(long long)__ldg(row_tab + m) + (long long)n * col_stride] = acc;
-        else
-            C[(size_t)m * ldc + n] = acc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (size_t base = (size_t)blockIdx.x * 32; base < total; base += (size_t)gridDim.x * 32) {
+        const size_t i = base + lane;
+        float acc = 0.f;
+        if (i < total)
+            for (int s = warp; s < splits; s += 8) acc += partial[(size_t)s * total + i];
+        red[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && i < total) {
+            acc = red[0][lane];
+#pragma unroll
+            for (int w = 1; w < 8; w++) acc += red[w][lane];
+            const int m = (int)(i / N), n = (int)(i % N);
+            if (bias) acc += __ldg(bias + n);
+            if (relu) acc = fmaxf(acc, 0.f);
+            if (row_tab)
+                C[(long long)__ldg(row_tab + m) + (long long)n * col_stride] = acc;
+            else
+                C[(size_t)m * ldc + n] = acc;
+        }
+        __syncthreads();
     }
 }
 
@@ -542,10 +691,9 @@ int fill_operand(const b2rl_gemm_operand *src, int rows, int K, Operand *dst, co
     dst->mode = src->mode;
     dst->ld = src->ld;
     dst->vec = 0;
-    dst->row_tab = (const int2 *)src->row_tab;
-    dst->k_tab = (const int2 *)src->k_tab;
+    dst->row_off = src->row_off, dst->row_yx = src->row_yx;
+    dst->k_off = src->k_off, dst->k_yx = src->k_yx;
     dst->y_limit = src->y_limit, dst->x_limit = src->x_limit;
-    dst->shift = src->shift, dst->pitch = src->pitch;
     dst->along_k = src->lanes_along_k ? 1 : 0;
     dst->u8 = src->u8 ? 1 : 0;
     dst->scale = src->scale;
@@ -560,12 +708,14 @@ int fill_operand(const b2rl_gemm_operand *src, int rows, int K, Operand *dst, co
         dst->vec = (((uintptr_t)src->data & 15) == 0 && src->ld % 4 == 0);
         break;
     case B2RL_GEMM_GATHER:
-        B2RL_REQUIRE(src->row_tab && src->k_tab, B2RL_ERR_INVALID,
-                     "gemm: gather operand %s needs its row and k tables", name);
-        B2RL_REQUIRE(((uintptr_t)src->row_tab & 7) == 0 && ((uintptr_t)src->k_tab & 7) == 0,
-                     B2RL_ERR_INVALID, "gemm: tables of %s must be 8-byte aligned", name);
-        B2RL_REQUIRE(src->shift >= 0 && src->shift < 8 && src->y_limit > 0 && src->x_limit > 0,
-                     B2RL_ERR_RANGE, "gemm: gather geometry of %s out of range", name);
+        B2RL_REQUIRE(src->row_off && src->k_off, B2RL_ERR_INVALID,
+                     "gemm: gather operand %s needs its row and k offset tables", name);
+        B2RL_REQUIRE((src->row_yx == nullptr) == (src->k_yx == nullptr), B2RL_ERR_INVALID,
+                     "gemm: gather operand %s: coordinates on both tables or on none", name);
+        B2RL_REQUIRE(((uintptr_t)src->k_off & 15) == 0 && ((uintptr_t)src->k_yx & 15) == 0,
+                     B2RL_ERR_INVALID, "gemm: k tables of %s must be 16-byte aligned", name);
+        B2RL_REQUIRE(!src->row_yx || (src->y_limit > 0 && src->x_limit > 0), B2RL_ERR_RANGE,
+                     "gemm: gather limits of %s out of range", name);
         break;
     default:
         B2RL_REQUIRE(false, B2RL_ERR_INVALID, "gemm: unknown operand mode %d", src->mode);
@@ -574,6 +724,16 @@ int fill_operand(const b2rl_gemm_operand *src, int rows, int K, Operand *dst, co
 }
 
 } // namespace
+
+static unsigned long long *g_gemm_times = nullptr; // debug: set by b2rl_gemm_debug_times
+
+// Debug aid (tools/gemm_phases.py): stamps of the phases of every CTA of the next launches go
+// to `device_buffer` (8 x uint64 per CTA, large enough for the largest grid); NULL switches off.
+extern "C" int b2rl_gemm_debug_times(void *device_buffer)
+{
+    g_gemm_times = (unsigned long long *)device_buffer;
+    return B2RL_OK;
+}
 
 extern "C" int64_t b2rl_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K)
 {
@@ -603,6 +763,7 @@ extern "C" int b2rl_gemm_tf32x3_ex(const b2rl_gemm_operand *A, const b2rl_gemm_o
     g.M = M, g.N = N, g.K = K, g.ldc = C->ld;
     g.c_vec = (!C->row_tab && ((uintptr_t)C->data & 15) == 0 && C->ld % 4 == 0);
     g.relu = C->relu ? 1 : 0;
+    g.times = g_gemm_times;
     g.bn = n_tile(N);
     plan_splits(M, N, K, &g.splits, &g.kb_per_split);
     g.partial = nullptr;
@@ -633,8 +794,8 @@ extern "C" int b2rl_gemm_tf32x3_ex(const b2rl_gemm_operand *A, const b2rl_gemm_o
     B2RL_CUDA(cudaGetLastError());
     if (g.splits > 1) {
         const long long total = (long long)M * N;
-        long long blocks = (total + 255) / 256;
-        if (blocks > 4ll * sm_count_cached()) blocks = 4ll * sm_count_cached();
+        long long blocks = (total + 31) / 32;
+        if (blocks > 8ll * sm_count_cached()) blocks = 8ll * sm_count_cached();
         k_gemm_reduce<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
             g.partial, g.splits, M, N, C->bias, g.relu, C->data, C->ld, C->row_tab,
             C->col_stride);

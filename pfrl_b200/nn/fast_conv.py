@@ -4,8 +4,9 @@
 same state_dict keys).  On CUDA, for contiguous fp32 [N, 4, 84, 84] inputs
 that do not require grad (observations), the forward runs
 ``b2rl_conv_nature1_fwd`` (csrc/conv.cu: exact fp32 FFMA accumulation, several
-times faster than cuDNN's TF32-off path); the weight gradient is a tensor-core implicit GEMM
-(ops/conv.py, read straight from the bytes for uint8 inputs).  uint8 inputs (phi = utils.phi.RawU8: the replay gather
+times faster than cuDNN's TF32-off path); the weight gradient comes from
+``aten::convolution_backward`` (cuDNN), or with B2RL_CONV=tcgen05 from the tensor-core
+implicit GEMM of ops/conv.py (read straight from the bytes for uint8 inputs; slower today).  uint8 inputs (phi = utils.phi.RawU8: the replay gather
 emits bytes) go through ``b2rl_conv_nature1_fwd_u8``, which applies ``x * input_scale``
 while it stages the image, so the f32 batch is never written to HBM.  Everything else
 falls through to cuDNN.
@@ -39,7 +40,7 @@ class _Conv1Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
-        if conv_ops.enabled() and x.shape[0] >= 8:
+        if conv_ops.mode() == "tcgen05" and x.shape[0] >= 8:
             gw = conv_ops.geometry(x.shape[0], 4, 84, 84, 32, 8, 8, 4, str(x.device)) \
                 .wgrad(x, grad_out)
             return None, gw, grad_out.sum((0, 2, 3)) if ctx.has_bias else None
@@ -73,7 +74,7 @@ class _Conv1U8Fn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
-        if conv_ops.enabled() and x.shape[0] >= 8:
+        if conv_ops.mode() == "tcgen05" and x.shape[0] >= 8:
             # tensor-core weight gradient straight from the bytes (ops/conv.py)
             gw = conv_ops.geometry(x.shape[0], 4, 84, 84, 32, 8, 8, 4, str(x.device)) \
                 .wgrad(x, grad_out, scale=ctx.scale)

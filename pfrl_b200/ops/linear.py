@@ -8,9 +8,9 @@ place whatever their orientation (row stride = leading dimension), so the halves
 ``torch.chunk`` and the transposed backward products need no copies.
 
 Replaces the F.linear calls of pfrl/q_functions/dueling_dqn.py:67-129,
-pfrl/nn/noisy_linear.py:53-70 and pfrl/nn/atari_cnn.py:17-47.  ``B2RL_LINEAR=cublas`` in the
-environment switches the layers back to cuBLAS (A/B timing); anything that is not a 2-D
-fp32 CUDA product of a useful size goes to ``F.linear`` as well.
+pfrl/nn/noisy_linear.py:53-70 and pfrl/nn/atari_cnn.py:17-47.  Which products take the
+tensor-core path is decided by ``worth_it`` (measured break-even against cuBLAS fp32);
+``B2RL_LINEAR=cublas`` / ``=tcgen05`` in the environment force one side (A/B timing).
 """
 import ctypes
 import os
@@ -21,8 +21,16 @@ import torch.nn.functional as F
 
 from pfrl_b200 import _lib
 
-#: products smaller than this many multiply-adds are launch-bound either way: left to cuBLAS
-MIN_MACS = 1 << 22
+def worth_it(M, N, K):
+    """Products that measured faster than cuBLAS' fp32 SGEMM on B200 (tools/bench_gemm.py):
+    the 3136-deep layers at any batch, and everything from ~0.5 G multiply-adds up; the
+    small heads (512 x 918 x 512 and the like) are launch- and epilogue-bound and stay on
+    cuBLAS.  B2RL_LINEAR=tcgen05 forces the tensor-core path, =cublas forbids it."""
+    forced = os.environ.get("B2RL_LINEAR", "auto")
+    if forced == "tcgen05":
+        return True
+    macs = M * N * K
+    return forced != "cublas" and ((K >= 1024 and macs >= 1 << 24) or macs >= 1 << 29)
 
 
 def _rows(t):
@@ -67,27 +75,30 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight = ctx.saved_tensors
+        batch, n_out, n_in = x.shape[0], weight.shape[0], weight.shape[1]
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             # dX[batch, in] = dY[batch, out] . W[out, in]: W is read with `out` as the row index
-            gx = gemm(grad_out, weight.detach(), b_mn_major=True)
+            if worth_it(batch, n_in, n_out):
+                gx = gemm(grad_out, weight.detach(), b_mn_major=True)
+            else:
+                gx = grad_out @ weight.detach()
         if ctx.needs_input_grad[1]:
             # dW[out, in] = dY^T . X: both read with the batch index as the row index
-            gw = gemm(grad_out, x.detach(), a_mn_major=True, b_mn_major=True)
+            if worth_it(n_out, n_in, batch):
+                gw = gemm(grad_out, x.detach(), a_mn_major=True, b_mn_major=True)
+            else:
+                gw = grad_out.t() @ x.detach()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = grad_out.sum(0)
         return gx, gw, gb
-
-
-def enabled():
-    return os.environ.get("B2RL_LINEAR", "tcgen05") != "cublas"
 
 
 def linear(x, weight, bias=None):
     """F.linear; 2-D fp32 CUDA products of a useful size run on the tensor cores."""
     if (x.is_cuda and x.ndim == 2 and x.dtype == torch.float32 and weight.dtype == torch.float32
             and weight.ndim == 2 and (bias is None or bias.dtype == torch.float32)
-            and x.shape[0] * weight.shape[0] * weight.shape[1] >= MIN_MACS and enabled()):
+            and worth_it(x.shape[0], weight.shape[0], weight.shape[1])):
         return _LinearFn.apply(x, weight, bias)
     return F.linear(x, weight, bias)
 

@@ -77,9 +77,11 @@ def test_conv1_on_raw_uint8_frames():
     assert _rel(gw, gw64) < 1e-5
 
 
-def test_tcconv2d_module_autograd_matches_cudnn():
+@pytest.mark.parametrize("policy", ["auto", "tcgen05"])
+def test_tcconv2d_module_autograd_matches_cudnn(monkeypatch, policy):
     from pfrl_b200.ops.conv import TCConv2d
 
+    monkeypatch.setenv("B2RL_CONV", policy)
     torch.manual_seed(0)
     m = TCConv2d(32, 64, 4, stride=2).cuda()
     x = torch.randn(64, 32, 20, 20, device="cuda", requires_grad=True)

@@ -135,6 +135,10 @@ def test_rainbow_head_uses_the_tensor_core_path(monkeypatch):
     calls = []
     real = lin.gemm
     monkeypatch.setattr(lin, "gemm", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    q(x)
+    assert len(calls) == 1  # default policy: the 3136-deep main_stream only (ops.linear.worth_it)
+    calls.clear()
+    monkeypatch.setenv("B2RL_LINEAR", "tcgen05")
     out_tc = q(x).q_values
     assert len(calls) == 3  # main_stream, a_stream, v_stream
     monkeypatch.setenv("B2RL_LINEAR", "cublas")
@@ -142,7 +146,7 @@ def test_rainbow_head_uses_the_tensor_core_path(monkeypatch):
     assert (out_tc - out_cb).abs().max() < 1e-5
     # noisy layers (fresh noise per call: compare with the same generator state)
     to_factorized_noisy(q, sigma_scale=0.5)
-    monkeypatch.delenv("B2RL_LINEAR")
+    monkeypatch.setenv("B2RL_LINEAR", "tcgen05")
     torch.manual_seed(1)
     n_before = len(calls)
     o1 = q(x).q_values
