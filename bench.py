@@ -257,6 +257,60 @@ def rainbow_loop(agent, env, vec_steps):
         obss = env.reset(np.logical_not(dones))
 
 
+def k10_record():
+    """The tensor-core path (csrc/gemm.cu, tcgen05 3xTF32, fp32 results) on the Rainbow layers
+    at B = 512 against the fp32 library calls the reference configuration makes (TF32 off):
+    median of 20 event-timed calls each, L2 flushed in between."""
+    import torch
+    import torch.nn.functional as F
+
+    from pfrl_b200.ops.conv import geometry
+    from pfrl_b200.ops.linear import gemm
+
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
+
+    def t_us(fn, reps=20):
+        for _ in range(3):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(reps)]
+        for a, b in evs:
+            flush.add_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return round(ts[len(ts) // 2] * 1e3, 1)
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    x = torch.randn(512, 3136, device="cuda")
+    w = torch.randn(1024, 3136, device="cuda")
+    gy = torch.randn(512, 1024, device="cuda")
+    out = {"arithmetic": "fp32 in / fp32 out, 3 x TF32 split on tcgen05.mma.kind::tf32",
+           "main_stream_fwd_512x1024x3136_us": {"tcgen05": t_us(lambda: gemm(x, w)),
+                                                "cublas_fp32": t_us(lambda: x @ w.t())},
+           "main_stream_dX_us": {"tcgen05": t_us(lambda: gemm(gy, w, b_mn_major=True)),
+                                 "cublas_fp32": t_us(lambda: gy @ w)},
+           "main_stream_dW_us": {"tcgen05": t_us(lambda: gemm(gy, x, a_mn_major=True, b_mn_major=True)),
+                                 "cublas_fp32": t_us(lambda: gy.t() @ x)}}
+    xc = torch.rand(512, 32, 20, 20, device="cuda")
+    wc = torch.randn(64, 32, 4, 4, device="cuda") * 0.05
+    geo = geometry(512, 32, 20, 20, 64, 4, 4, 2, "cuda:0")
+    out["conv2_fwd_512x32x20x20_us"] = {"tcgen05": t_us(lambda: geo.forward(xc, wc)),
+                                         "cudnn_fp32": t_us(lambda: F.conv2d(xc, wc, stride=2))}
+    x3 = torch.rand(512, 64, 9, 9, device="cuda")
+    w3 = torch.randn(64, 64, 3, 3, device="cuda") * 0.05
+    g3 = torch.randn(512, 64, 7, 7, device="cuda")
+    geo3 = geometry(512, 64, 9, 9, 64, 3, 3, 1, "cuda:0")
+    out["conv3_dgrad_us"] = {
+        "tcgen05": t_us(lambda: geo3.dgrad(g3, w3)),
+        "cudnn_fp32": t_us(lambda: torch.ops.aten.convolution_backward(
+            g3, x3, w3, None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1, [True, False, False]))}
+    return out
+
+
 def best_torch_threads():
     import torch
     from oracle.pyport_rainbow import RainbowNet
@@ -577,7 +631,7 @@ def main():
 
         torch.backends.cudnn.allow_tf32 = False  # fp32 parity configuration
         torch.backends.cuda.matmul.allow_tf32 = False
-        graph = (not args.no_rainbow_graph) and world == 1
+        graph = not args.no_rainbow_graph  # N > 1: two graphs around the eager all-reduce
         agent = make_rainbow_agent(buf, local_rank, B,
                                    grad_sync=parallel.GradSync() if world > 1 else None,
                                    cuda_graph=graph)
@@ -585,7 +639,7 @@ def main():
         res = {}
         for tag, env_dev in (("value", dev), ("e2e", "cpu")):
             env = SyntheticAtariVectorEnv(RAINBOW_ENVS, device=env_dev, seed=11 + rank)
-            rainbow_loop(agent, env, 4)  # warm-up (cuDNN autotune, allocator, graph capture)
+            rainbow_loop(agent, env, 8)  # warm-up: cuDNN autotune, allocator, graph captures (first 4), then steady state
             barrier()
             a, b = ev(), ev()
             n0 = agent.optim_t
@@ -606,6 +660,10 @@ def main():
             secondary = bench_secondary.run_all(graph=True)
         except Exception as exc:  # secondary lines never take the headline down
             secondary = {"error": repr(exc)}
+        try:
+            secondary["k10_tensor_cores"] = k10_record()
+        except Exception as exc:
+            secondary["k10_tensor_cores"] = {"error": repr(exc)}
 
     clk = clocks.stop() if rank == 0 else None
 
@@ -710,6 +768,9 @@ def main():
             "observations": "uint8 minibatches out of the replay gather; x / 255 applied inside "
                             "conv1 (b2rl_conv_nature1_fwd_u8), same numbers as f32 batches",
             "model": "DistributionalDuelingDQN(18, 51) + factorized noisy, Adam(6.25e-5)",
+            "dense_layers": "tcgen05 3xTF32 (k_gemm_tf32x3) for main_stream fwd/dX/dW, conv2 forward, "
+                            "conv3 input gradient; cuDNN / cuBLAS fp32 where they measured faster; "
+                            "conv1 forward own FFMA kernel",
             "note": "value: GPU-resident synthetic env; e2e: host numpy env (frames H2D, "
                     "actions D2H); gradient all-reduce (NCCL) when n_gpus > 1"}
     if secondary is not None:

@@ -176,10 +176,15 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
         # Optional: replay forward(s) + fused loss + backward + clip + optimizer
         # step as ONE CUDA graph (pays off when the minibatch is small and the
         # update is launch-bound, e.g. Nature-DQN at batch 32).
+        # With a grad_sync hook (data-parallel ranks) the update is TWO graphs around the
+        # eagerly issued all-reduce: forward + loss + backward + bucket packing, then
+        # unpacking + clipping + optimizer step.
         self._graph_enabled = bool(cuda_graph) and self.device.type == "cuda" \
-            and grad_sync is None
+            and (grad_sync is None or all(hasattr(grad_sync, a) for a in ("pack", "reduce", "unpack")))
         self._graph = None
         self._graph_warmup = 0
+        self._act_graph = None
+        self._act_graph_warmup = 0
         if self._graph_enabled:
             for group in optimizer.param_groups:
                 if "capturable" in group:
@@ -252,14 +257,31 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
             self._static_in = {k: v.clone() for k, v in exp_batch.items()}
             torch.cuda.synchronize(self.device)
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._static_out = self._learn(self._static_in, want_errors)
+            if self.grad_sync is None:
+                with torch.cuda.graph(self._graph):
+                    self._static_out = self._learn(self._static_in, want_errors)
+            else:
+                with torch.cuda.graph(self._graph):
+                    loss, delta = self._compute_loss(self._static_in, want_errors=want_errors)
+                    self.optimizer.zero_grad()
+                    loss.backward()
+                    self.grad_sync.pack(self.model)
+                    self._static_out = (loss.detach(), delta)
+                self._graph_step = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph_step, pool=self._graph.pool()):
+                    self.grad_sync.unpack(self.model)
+                    if self.max_grad_norm is not None:
+                        clip_l2_grad_norm_(self.model.parameters(), self.max_grad_norm)
+                    self.optimizer.step()
             self._static_q = self._last_q
         if sig != self._graph_sig:
             return self._learn(exp_batch, want_errors)  # different batch layout: run eagerly
         for k, v in exp_batch.items():
             self._static_in[k].copy_(v)
         self._graph.replay()  # capture only records: every update is a replay
+        if self.grad_sync is not None:
+            self.grad_sync.reduce(self.model)  # NCCL, eager, between the two graphs
+            self._graph_step.replay()
         self._last_q = self._static_q
         return self._static_out
 
@@ -316,10 +338,42 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
     def _evaluate_model(self, batch_obs):
         return self.model(self.batch_states(batch_obs, self.device, self.phi))
 
+    def _greedy_graphed(self, batch_obs):
+        """Acting forward (a few dozen tiny launches at num_envs images) replayed as one CUDA
+        graph: observations are copied into a static buffer, the greedy actions come back in
+        one.  Falls back to the eager call while warming up or when the batch layout changes."""
+        x = self.batch_states(batch_obs, self.device, self.phi)
+        if not isinstance(x, torch.Tensor):
+            return None
+        sig = (tuple(x.shape), x.dtype)
+        if self._act_graph is None:
+            if self._act_graph_warmup < 3:
+                self._act_graph_warmup += 1
+                return None
+            self._act_sig = sig
+            self._act_in = x.clone()
+            torch.cuda.synchronize(self.device)
+            self._act_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._act_graph):
+                self._act_av = self.model(self._act_in)
+                self._act_out = self._act_av.greedy_actions
+        if sig != self._act_sig:
+            return None
+        self._act_in.copy_(x)
+        self._act_graph.replay()
+        return self._act_av, self._act_out
+
     def batch_act(self, batch_obs):
         with torch.no_grad(), evaluating(self.model):
-            batch_av = self._evaluate_model(batch_obs)
-            batch_argmax = batch_av.greedy_actions.detach().cpu().numpy()
+            graphed = None
+            if self._graph_enabled and type(self)._evaluate_model is DQN._evaluate_model:
+                graphed = self._greedy_graphed(batch_obs)
+            if graphed is not None:
+                batch_av, greedy = graphed
+                batch_argmax = greedy.cpu().numpy()
+            else:
+                batch_av = self._evaluate_model(batch_obs)
+                batch_argmax = batch_av.greedy_actions.detach().cpu().numpy()
         if not self.training:
             return batch_argmax
         batch_action = [

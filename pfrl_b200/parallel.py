@@ -83,19 +83,33 @@ class GradSync:
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         return bool(int(t.item()))
 
-    def __call__(self, module):
-        w = world_size()
-        if w == 1:
-            return
+    # The three stages are separate so that an agent can replay pack / unpack inside CUDA graphs
+    # and issue only the collective itself eagerly between them (agents/dqn.py).
+    def pack(self, module):
+        """Gradients -> the flat bucket (one multi-tensor copy)."""
         flat, views, params = self._bucket(module)
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
         torch._foreach_copy_(views, grads)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        flat.div_(w)
+
+    def reduce(self, module):
+        """The collective: SUM over ranks of the flat bucket."""
+        dist.all_reduce(self._bucket(module)[0], op=dist.ReduceOp.SUM)
+
+    def unpack(self, module):
+        """Bucket / world -> the gradients."""
+        flat, views, params = self._bucket(module)
+        flat.div_(world_size())
         for p, v in zip(params, views):
             if p.grad is None:
                 p.grad = v.clone()
         torch._foreach_copy_([p.grad for p in params], views)
+
+    def __call__(self, module):
+        if world_size() == 1:
+            return
+        self.pack(module)
+        self.reduce(module)
+        self.unpack(module)
 
 
 def sync_advantage_stats(adv):
