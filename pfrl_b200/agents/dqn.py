@@ -387,6 +387,14 @@ class DQN(agent.AttributeSavingMixin, agent.BatchAgent):
 
     def _batch_observe_train(self, batch_obs, batch_reward, batch_done, batch_reset):
         # per-env interleaving of append and update exactly as dqn.py:509-549
+        # (device-resident envs hand out CUDA tensors: one D2H copy per vector step instead of
+        # a stream synchronisation per environment and field)
+        if isinstance(batch_reward, torch.Tensor):
+            batch_reward = batch_reward.detach().cpu().numpy()
+        if isinstance(batch_done, torch.Tensor):
+            batch_done = batch_done.detach().cpu().numpy()
+        if isinstance(batch_reset, torch.Tensor):
+            batch_reset = batch_reset.detach().cpu().numpy()
         for i in range(len(batch_obs)):
             self.t += 1
             self._cumulative_steps += 1

@@ -619,15 +619,39 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tf32x3(const __grid_constan
     }
 }
 
-// C = sum over the K splits + bias, relu; dense or scattered like the epilogue.  A block of
-// 8 warps works on 32 consecutive outputs: warp w adds the splits w, w + 8, ... (coalesced
-// 128-byte reads), the eight partial sums meet in shared memory and are added in warp order --
-// the order of the additions never depends on timing, so results are run-to-run identical.
+// C = sum over the K splits + bias, relu; dense or scattered like the epilogue.  The order of
+// the additions never depends on timing, so results are run-to-run identical.
+// Large outputs: one thread per output, splits added in order (coalesced across the threads).
 __global__ void __launch_bounds__(256) k_gemm_reduce(const float *__restrict__ partial, int splits,
                                                      int M, int N, const float *__restrict__ bias,
                                                      int relu, float *__restrict__ C, int ldc,
                                                      const int *__restrict__ row_tab,
                                                      int col_stride)
+{
+    const size_t total = (size_t)M * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (size_t)gridDim.x * blockDim.x) {
+        float acc = partial[i];
+        for (int s = 1; s < splits; s++) acc += partial[(size_t)s * total + i];
+        const int m = (int)(i / N), n = (int)(i % N);
+        if (bias) acc += __ldg(bias + n);
+        if (relu) acc = fmaxf(acc, 0.f);
+        if (row_tab)
+            C[(long long)__ldg(row_tab + m) + (long long)n * col_stride] = acc;
+        else
+            C[(size_t)m * ldc + n] = acc;
+    }
+}
+
+// Small outputs with many splits (the weight gradients: 32 K outputs, 36 splits): a block of
+// 8 warps works on 32 consecutive outputs, warp w adds the splits w, w + 8, ... (coalesced
+// 128-byte reads), the eight partial sums meet in shared memory and are added in warp order.
+__global__ void __launch_bounds__(256) k_gemm_reduce_deep(const float *__restrict__ partial,
+                                                          int splits, int M, int N,
+                                                          const float *__restrict__ bias, int relu,
+                                                          float *__restrict__ C, int ldc,
+                                                          const int *__restrict__ row_tab,
+                                                          int col_stride)
 {
     __shared__ float red[8][32];
     const size_t total = (size_t)M * N;
@@ -794,11 +818,19 @@ extern "C" int b2rl_gemm_tf32x3_ex(const b2rl_gemm_operand *A, const b2rl_gemm_o
     B2RL_CUDA(cudaGetLastError());
     if (g.splits > 1) {
         const long long total = (long long)M * N;
-        long long blocks = (total + 31) / 32;
-        if (blocks > 8ll * sm_count_cached()) blocks = 8ll * sm_count_cached();
-        k_gemm_reduce<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-            g.partial, g.splits, M, N, C->bias, g.relu, C->data, C->ld, C->row_tab,
-            C->col_stride);
+        if (total >= 65536 || g.splits <= 8) {
+            long long blocks = (total + 255) / 256;
+            if (blocks > 8ll * sm_count_cached()) blocks = 8ll * sm_count_cached();
+            k_gemm_reduce<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+                g.partial, g.splits, M, N, C->bias, g.relu, C->data, C->ld, C->row_tab,
+                C->col_stride);
+        } else {
+            long long blocks = (total + 31) / 32;
+            if (blocks > 8ll * sm_count_cached()) blocks = 8ll * sm_count_cached();
+            k_gemm_reduce_deep<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+                g.partial, g.splits, M, N, C->bias, g.relu, C->data, C->ld, C->row_tab,
+                C->col_stride);
+        }
         B2RL_CUDA(cudaGetLastError());
     }
     return B2RL_OK;
