@@ -51,7 +51,8 @@ def main():
     if os.path.exists(src):
         shutil.copy(src, os.path.join(PROF, "r02_launches_ncu.csv"))
 
-    caps = [("r02_step_exact", "step_exact"), ("r02_step_parallel", "step_parallel"),
+    caps = [("r02_step_exact", "step_exact"), ("r02_step_tail", "step_parallel:1"),
+            ("r02_step_tail", "step_parallel_u8_out:3"),
             ("r02_sampler_v6", "sampler_v6"), ("r02_gather", "gather"),
             ("r02_update_multi", "update_multi"), ("r02_gemm", "gemm_tf32x3"), ("r02_gae", "gae"),
             ("r02_ppo_loss", "ppo_loss"), ("r02_polyak", "polyak"), ("r02_sac_target", "sac_target"),
