@@ -297,3 +297,25 @@ def test_td3_on_device_replay():
     stats = dict(agent.get_statistics())
     assert stats["q_func_n_updates"] > 200 and stats["policy_n_updates"] > 100
     assert np.isfinite(stats["average_q1"]) and np.isfinite(stats["average_policy_loss"])
+
+
+@pytest.mark.gpu
+def test_empirical_normalization_on_cuda_matches_reference_golden():
+    """pfrl/nn/empirical_normalization.py:61-105 on cuda:0 against the fixture the
+    real reference produced (the same one the CPU suite checks), tolerance 1e-5."""
+    import os
+
+    import numpy as np
+
+    from pfrl_b200.nn import EmpiricalNormalization
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "empirical_normalization.npz"))
+    en = EmpiricalNormalization(7, clip_threshold=5).cuda()
+    for i in range(4):
+        y = en(torch.tensor(g["x%d" % i], device="cuda"), update=True).cpu().numpy()
+        np.testing.assert_allclose(y, g["y%d" % i], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(en.mean.cpu().numpy(), g["mean"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(en.std.cpu().numpy(), g["std"], rtol=1e-6)
+    assert int(en.count) == int(g["count"])
+    out = en(torch.tensor(g["probe"], device="cuda"), update=False).cpu().numpy()
+    np.testing.assert_allclose(out, g["probe_out"], rtol=1e-5, atol=1e-6)
