@@ -275,6 +275,22 @@ int b2rl_step_times(b2rl_replay *h, uint64_t *out_ns_host, void *stream);
 int b2rl_per_defer_errors(b2rl_replay *h, const void *err_dev, int err_is_f64,
                           int32_t n, double alpha, double eps,
                           double error_min, double error_max);
+
+/* TD errors as HOST doubles (the reference's update_errors(list of Python floats),
+ * pfrl/replay_buffers/prioritized.py:47-55,125-126).  The priorities
+ *   (min(hi, max(lo, d)) + eps) ** alpha
+ * are computed on the host with libm's pow, the function behind CPython's float **, in the
+ * reference's operation order -- bit-identical to its list comprehension -- and must be > 0
+ * (collections/prioritized.py:109).  has_min / has_max = 0 stand for error_min / error_max =
+ * None.  defer = 0: write back now (one launch); defer = 1: fold the write-back into the
+ * next b2rl_replay_step like b2rl_per_defer_errors.  b2rl_host_priority_from_errors is the
+ * arithmetic alone (no device needed). */
+int b2rl_host_priority_from_errors(const double *err, int32_t n, double alpha, double eps,
+                                   int has_min, double error_min, int has_max,
+                                   double error_max, double *out);
+int b2rl_per_update_host_errors(b2rl_replay *h, const double *err_host, int32_t n,
+                                double alpha, double eps, int has_min, double error_min,
+                                int has_max, double error_max, int defer, void *stream);
 /* Apply a deferred write-back now (no-op if none is registered). */
 int b2rl_per_flush(b2rl_replay *h, void *stream);
 

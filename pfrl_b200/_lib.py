@@ -176,6 +176,8 @@ SIGNATURES = {
     "b2rl_replay_step": (_int, [_vp, ctypes.POINTER(StepArgs), _vp]),
     "b2rl_step_times": (_int, [_vp, _vp, _vp]),
     "b2rl_per_defer_errors": (_int, [_vp, _vp, _int, _i32, _dbl, _dbl, _dbl, _dbl]),
+    "b2rl_host_priority_from_errors": (_int, [_vp, _i32, _dbl, _dbl, _int, _dbl, _int, _dbl, _vp]),
+    "b2rl_per_update_host_errors": (_int, [_vp, _vp, _i32, _dbl, _dbl, _int, _dbl, _int, _dbl, _int, _vp]),
     "b2rl_per_flush": (_int, [_vp, _vp]),
     "b2rl_replay_gather": (
         _int, [_vp, _vp, _i32, _vp, _int, ctypes.c_float, ctypes.POINTER(BatchOut), _vp]),

@@ -577,6 +577,57 @@ extern "C" int b2rl_per_defer_errors(b2rl_replay *h, const void *err_dev, int er
     return B2RL_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Host TD errors (the reference's update_errors(list of Python floats),
+// replay_buffers/prioritized.py:47-55,125-126): the priorities are computed HERE on the host
+// with libm's pow -- the function behind CPython's float ** -- in the reference's operation
+// order (max(lo, d), min(hi, d), + eps, ** alpha), so they are bit-identical to the reference's
+// list comprehension; then staged to the device and either written back now or folded into
+// the next fused step like b2rl_per_defer_errors.
+// ---------------------------------------------------------------------------
+extern "C" int b2rl_host_priority_from_errors(const double *err, int32_t n, double alpha,
+                                              double eps, int has_min, double error_min,
+                                              int has_max, double error_max, double *out)
+{
+    B2RL_REQUIRE(err && out && n >= 0, B2RL_ERR_INVALID, "host_priority_from_errors: bad argument");
+    for (int32_t i = 0; i < n; i++) {
+        double d = err[i];
+        if (has_min) d = (d > error_min) ? d : error_min; // max(lo, d): lo unless d is larger
+        if (has_max) d = (d < error_max) ? d : error_max; // min(hi, d)
+        out[i] = pow(d + eps, alpha);
+    }
+    return B2RL_OK;
+}
+
+extern "C" int b2rl_per_update_host_errors(b2rl_replay *h, const double *err_host, int32_t n,
+                                           double alpha, double eps, int has_min,
+                                           double error_min, int has_max, double error_max,
+                                           int defer, void *stream)
+{
+    TRY(check_update(h, n));
+    B2RL_REQUIRE(err_host, B2RL_ERR_INVALID, "null errors");
+    cudaStream_t s = (cudaStream_t)stream;
+    B2RL_CUDA(cudaSetDevice(h->cfg.device));
+    TRY(b2rl_stage_acquire(h, (size_t)n * 8));
+    double *prio = reinterpret_cast<double *>(h->pin);
+    TRY(b2rl_host_priority_from_errors(err_host, n, alpha, eps, has_min, error_min, has_max,
+                                       error_max, prio));
+    for (int i = 0; i < n; i++)
+        B2RL_REQUIRE(prio[i] > 0.0, B2RL_ERR_INVALID,
+                     "priority[%d]=%g must be > 0 (collections/prioritized.py:109)", i, prio[i]);
+    B2RL_CUDA(cudaMemcpyAsync(h->new_prio, h->pin, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    TRY(b2rl_stage_release(h, s));
+    if (!defer) return launch_update(h, n, nullptr, 0, 0, 0, 0, 0, s);
+    h->pending = true;
+    h->pend_err = nullptr; // priorities are already in new_prio
+    h->pend_is_f64 = 0;
+    h->pend_n = n;
+    h->pend_alpha = h->pend_eps = h->pend_emin = h->pend_emax = 0.0;
+    h->wait_priority = false; // the sample is answered; the write-back is owed
+    h->last_n = 0;
+    return B2RL_OK;
+}
+
 int b2rl_flush_pending(b2rl_replay *h, cudaStream_t s)
 {
     if (!h->pending) return B2RL_OK;

@@ -655,6 +655,20 @@ class PrioritizedReplayBuffer(DeviceNStepBuffer, PriorityWeightError):
             else:
                 self.store.update_errors(e.contiguous().view(-1), self.alpha, self.eps,
                                          self.error_min, self.error_max)
+        elif hasattr(self.store, "update_host_errors"):
+            # host floats: the reference's list comprehension (max / min / + eps / ** alpha in
+            # Python floats) evaluated inside the library with the same libm pow, one call;
+            # with the fused step planned, the write-back rides on the next launch
+            if isinstance(errors, torch.Tensor):
+                errors = errors.detach().cpu().numpy()
+            try:
+                self.store.update_host_errors(
+                    errors, self.alpha, self.eps, self.error_min, self.error_max,
+                    defer=self.fused and self._plan is not None)
+            except _lib.B2rlError as exc:
+                if "must be > 0" in str(exc):
+                    raise AssertionError(str(exc))  # collections/prioritized.py:109
+                raise
         else:
             if isinstance(errors, torch.Tensor):
                 errors = errors.tolist()

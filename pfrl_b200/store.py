@@ -23,6 +23,16 @@ def _stream(device=None):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+_ITEMSIZE = {}
+
+
+def _itemsize(dtype):
+    sz = _ITEMSIZE.get(dtype)
+    if sz is None:
+        sz = _ITEMSIZE[dtype] = torch.empty((), dtype=dtype).element_size()
+    return sz
+
+
 class DeviceReplayStore:
     """HBM part ring + experience records (+ fp64 sum/min trees)."""
 
@@ -174,6 +184,19 @@ class DeviceReplayStore:
             errors.numel(), float(alpha), float(eps), float(error_min), float(error_max)))
         self._deferred_errors = errors
 
+    def update_host_errors(self, errors, alpha, eps, error_min, error_max, defer):
+        """TD errors as host floats -> priorities with the reference's Python-float arithmetic
+        (libm pow, computed inside the library) -> write-back now, or folded into the next
+        fused step (defer)."""
+        e = np.ascontiguousarray(errors, dtype=np.float64)
+        _lib.check(self.L.b2rl_per_update_host_errors(
+            self.h, _np_ptr(e), e.shape[0], float(alpha), float(eps),
+            int(error_min is not None), 0.0 if error_min is None else float(error_min),
+            int(error_max is not None), 0.0 if error_max is None else float(error_max),
+            int(bool(defer)), _stream(self.device)))
+        if defer:
+            self._deferred_errors = None
+
     def flush(self):
         _lib.check(self.L.b2rl_per_flush(self.h, _stream(self.device)))
         self._deferred_errors = None
@@ -198,21 +221,30 @@ class DeviceReplayStore:
                     odt, oshape = torch.float32, (n, obs_bytes)
                 else:
                     odt = obs_dtype or torch.uint8
-                    oshape = (n, obs_bytes // torch.empty((), dtype=odt).element_size())
+                    oshape = (n, obs_bytes // _itemsize(odt))
                 out["state"] = torch.empty(oshape, dtype=odt, device=dev)
                 out["next_state"] = torch.empty(oshape, dtype=odt, device=dev)
-            asz = torch.empty((), dtype=action_dtype).element_size()
-            out["action"] = torch.empty((n, self.action_bytes // asz), dtype=action_dtype, device=dev)
-            out["reward"] = torch.empty(n, dtype=torch.float32, device=dev)
-            out["is_state_terminal"] = torch.empty(n, dtype=torch.float32, device=dev)
-            out["discount"] = torch.empty(n, dtype=torch.float32, device=dev)
-            out["weights"] = torch.empty(n, dtype=torch.float32, device=dev)
+            # the small per-sample outputs share ONE allocation (the call sits on the host's
+            # critical path between two launches: every torch.empty costs a few microseconds)
+            asz = _itemsize(action_dtype)
+            small = [("action", action_dtype, (n, self.action_bytes // asz)),
+                     ("reward", torch.float32, (n,)), ("is_state_terminal", torch.float32, (n,)),
+                     ("discount", torch.float32, (n,)), ("weights", torch.float32, (n,))]
             if want_index:
-                out["index"] = torch.empty(n, dtype=torch.int64, device=dev)
+                small.append(("index", torch.int64, (n,)))
             if want_priority:
-                out["priority"] = torch.empty(n, dtype=torch.float64, device=dev)
+                small.append(("priority", torch.float64, (n,)))
             if want_prob:
-                out["prob"] = torch.empty(n, dtype=torch.float64, device=dev)
+                small.append(("prob", torch.float64, (n,)))
+            sizes = []
+            for _, dt, shp in small:
+                count = shp[0] * (shp[1] if len(shp) > 1 else 1)
+                sizes.append(count * _itemsize(dt))
+            slab = torch.empty(sum((nb + 15) & ~15 for nb in sizes), dtype=torch.uint8, device=dev)
+            off = 0
+            for (name, dt, shp), nb in zip(small, sizes):
+                out[name] = slab[off:off + nb].view(dt).view(shp)
+                off += (nb + 15) & ~15
         ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
         if isinstance(u, torch.Tensor):
             assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous()
@@ -268,7 +300,7 @@ class DeviceReplayStore:
             odt, oshape = torch.float32, (n, obs_bytes)
         else:
             odt = obs_dtype or torch.uint8
-            oshape = (n, obs_bytes // torch.empty((), dtype=odt).element_size())
+            oshape = (n, obs_bytes // _itemsize(odt))
         out = {}
         if want_obs:
             out["state"] = torch.empty(oshape, dtype=odt, device=dev)

@@ -65,3 +65,37 @@ def test_oracle_builds_and_is_not_imported_by_the_product():
     hits = subprocess.run(["grep", "-rl", "--include=*.py", "-E", r"^\s*(from|import) oracle",
                            os.path.join(ROOT, "pfrl_b200")], capture_output=True, text=True)
     assert hits.stdout.strip() == ""
+
+
+def test_host_priority_arithmetic_is_bit_identical_to_python_floats():
+    """b2rl_host_priority_from_errors (libm pow inside the library) == the reference's list
+    comprehension in Python floats (pfrl/replay_buffers/prioritized.py:47-55), bit for bit:
+    this is what update_errors(host list) feeds the trees with."""
+    import ctypes
+
+    import numpy as np
+
+    from pfrl_b200 import _lib
+
+    L = _lib.load()
+    rng = np.random.RandomState(0)
+    err = np.concatenate([np.abs(rng.randn(20000)), rng.rand(20000) * 1e-3, rng.randn(5000) * 5,
+                          np.array([0.0, 1.0, 1e-300, 0.5, 2.0, 123456.789])])
+    for alpha, eps, lo, hi in ((0.5, 0.01, 0, 1), (0.6, 0.01, 0, 1), (0.7, 1e-6, None, None),
+                               (1.0, 0.01, 0, None), (0.5, 0.01, None, 3.5)):
+        want = []
+        for d in err.tolist():
+            if lo is not None:
+                d = max(lo, d)
+            if hi is not None:
+                d = min(hi, d)
+            want.append((d + eps) ** alpha if d + eps > 0 else float("nan"))
+        got = np.empty_like(err)
+        rc = L.b2rl_host_priority_from_errors(
+            err.ctypes.data_as(ctypes.c_void_p), len(err), alpha, eps, int(lo is not None),
+            0.0 if lo is None else float(lo), int(hi is not None), 0.0 if hi is None else float(hi),
+            got.ctypes.data_as(ctypes.c_void_p))
+        assert rc == 0
+        want = np.asarray(want, dtype=np.float64)
+        ok = np.isfinite(want)
+        assert np.array_equal(got[ok].view(np.uint64), want[ok].view(np.uint64)), (alpha, eps, lo, hi)
