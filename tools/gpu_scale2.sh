@@ -1,10 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 900 python -m pytest tests/test_agents_gpu.py tests/test_agent_traces_gpu.py tests/test_train_driver_gpu.py -q -x > gpurun_out/agents_test.log 2>&1
-echo "agent tests rc=$?"; tail -2 gpurun_out/agents_test.log
-timeout -s KILL 900 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/scale_n1.log 2>&1
+timeout -s KILL 900 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/scale_n1.log 2>&1
 echo "n1 rc=$?"
-timeout -s KILL 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/scale_n2.log 2>&1
+timeout -s KILL 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/scale_n2.log 2>&1
 echo "n2 rc=$?"
 python - <<'PY'
 import json
