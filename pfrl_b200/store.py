@@ -224,27 +224,19 @@ class DeviceReplayStore:
                     oshape = (n, obs_bytes // _itemsize(odt))
                 out["state"] = torch.empty(oshape, dtype=odt, device=dev)
                 out["next_state"] = torch.empty(oshape, dtype=odt, device=dev)
-            # the small per-sample outputs share ONE allocation (the call sits on the host's
-            # critical path between two launches: every torch.empty costs a few microseconds)
+            # the call sits on the host's critical path between two launches and every torch op
+            # costs 3-5 us there: the four f32 vectors come out of one [4, n] allocation with
+            # one unbind (slice + view chains measured slower than separate torch.empty calls)
+            (out["reward"], out["is_state_terminal"], out["discount"],
+             out["weights"]) = torch.empty((4, n), dtype=torch.float32, device=dev).unbind(0)
             asz = _itemsize(action_dtype)
-            small = [("action", action_dtype, (n, self.action_bytes // asz)),
-                     ("reward", torch.float32, (n,)), ("is_state_terminal", torch.float32, (n,)),
-                     ("discount", torch.float32, (n,)), ("weights", torch.float32, (n,))]
+            out["action"] = torch.empty((n, self.action_bytes // asz), dtype=action_dtype, device=dev)
             if want_index:
-                small.append(("index", torch.int64, (n,)))
+                out["index"] = torch.empty(n, dtype=torch.int64, device=dev)
             if want_priority:
-                small.append(("priority", torch.float64, (n,)))
+                out["priority"] = torch.empty(n, dtype=torch.float64, device=dev)
             if want_prob:
-                small.append(("prob", torch.float64, (n,)))
-            sizes = []
-            for _, dt, shp in small:
-                count = shp[0] * (shp[1] if len(shp) > 1 else 1)
-                sizes.append(count * _itemsize(dt))
-            slab = torch.empty(sum((nb + 15) & ~15 for nb in sizes), dtype=torch.uint8, device=dev)
-            off = 0
-            for (name, dt, shp), nb in zip(small, sizes):
-                out[name] = slab[off:off + nb].view(dt).view(shp)
-                off += (nb + 15) & ~15
+                out["prob"] = torch.empty(n, dtype=torch.float64, device=dev)
         ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
         if isinstance(u, torch.Tensor):
             assert u.is_cuda and u.dtype == torch.float64 and u.is_contiguous()
