@@ -775,7 +775,7 @@ def main():
                     "actions D2H); gradient all-reduce (NCCL) when n_gpus > 1"}
     if secondary is not None:
         line["secondary"] = secondary
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only
         r, rc = cpu_arm(cap, B, 10 ** 9, 2, args.cpu_seconds, 10.0 if rb is not None else None)
         if rc is not None:
             line["rainbow"]["cpu_baseline"] = {
