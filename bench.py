@@ -545,6 +545,16 @@ def main():
         return t0.elapsed_time(t1), {"write_back_us": ph[0] / 1e3, "sampling_us": ph[1] / 1e3,
                                      "gather_after_last_draw_us": ph[2] / 1e3,
                                      "launch_us": ph[3] / 1e3,
+                                     "write_back_phases_us_since_entry": {
+                                         "cta0_entries_collected": ph[31] / 1e3,
+                                         "cta0_subtree_stored": ph[32] / 1e3,
+                                         "cta0_arrival_ticket": ph[33] / 1e3,
+                                         "last_cta_roots_loaded": ph[34] / 1e3,
+                                         "last_cta_flag_released": ph[35] / 1e3,
+                                         **({"fine_cta0_unique_done": ph[28] / 1e3,
+                                             "fine_cta0_siblings_in": ph[29] / 1e3,
+                                             "fine_cta0_levels_done": ph[30] / 1e3}
+                                            if os.environ.get("B2RL_WB_FINE") else {})},
                                      **({"sampler_cycles_per_draw": {
                                          "main_wait_scout": ph[4] / B, "main_decide": ph[5] / B,
                                          "main_wait_queue": ph[6] / B, "main_loads": ph[7] / B,

@@ -262,8 +262,11 @@ int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *args, void *stream);
  * kernel leaves behind (synchronises `stream`): out_ns[0] deferred write-back,
  * [1] sampling (until the last draw is published), [2] gather tail (from there to the
  * exit of the last CTA), [3] the whole launch; [4..35] clock-cycle sums of the exact
- * sampler's pipeline segments when the library runs with B2RL_V6_CYCLES=1 (else 0).
- * out_ns_host has 36 entries.  Measurement aid (bench.py, tools/v6_cycles.py). */
+ * sampler's pipeline segments when the library runs with B2RL_V6_CYCLES=1 (else 0);
+ * [31..35] phases of the multi-CTA write-back in ns since CTA 0's entry: entries collected,
+ * subtree stored, arrival ticket taken (all CTA 0), subtree roots loaded, completion flag
+ * released (last CTA); with B2RL_WB_FINE=1 in the environment also [28..30]: CTA 0's sort /
+ * unique done, siblings fetched, level loop done.  out_ns_host has 36 entries.  Measurement aid (bench.py, tools/v6_cycles.py). */
 int b2rl_step_times(b2rl_replay *h, uint64_t *out_ns_host, void *stream);
 
 /* Answer the last sample with TD errors on the device WITHOUT launching: the

@@ -453,6 +453,7 @@ static int launch_update(b2rl_replay *h, int32_t n, const void *err, int err_is_
     a.nranges = 0;
     a.bump_n = 0;
     a.capacity = h->cfg.capacity;
+    a.stamps = nullptr;
     static int single_cta = -1; // B2RL_UPDATE=single keeps the one-CTA sorted-path kernel
     if (single_cta < 0) {
         const char *e = getenv("B2RL_UPDATE");

@@ -469,6 +469,7 @@ extern "C" int b2rl_replay_step(b2rl_replay *h, const b2rl_step_args *p, void *s
         a.u.nslots = h->nslots;
         a.upd_n = h->pend_n;
         a.upd_sync = h->ready_dev + 1;
+        a.u.stamps = h->times_dev + 3; // [3..7]: phases of the write-back
     }
     a.times = h->times_dev;
     // ---- gather
@@ -545,9 +546,17 @@ extern "C" int b2rl_step_times(b2rl_replay *h, uint64_t *out_ns, void *stream)
     out_ns[1] = t[2] - t[1];
     out_ns[2] = last > t[2] ? last - t[2] : 0;
     out_ns[3] = last - t[0];
+
     // [4, 36): clock64 sums of the exact sampler's pipeline segments (B2RL_V6_CYCLES=1)
     B2RL_CUDA(cudaMemcpyAsync(out_ns + 4, h->times_dev + 8 + 256, sizeof(uint64_t) * 32,
                               cudaMemcpyDeviceToHost, s));
     B2RL_CUDA(cudaStreamSynchronize(s));
+    // [31, 36): phases of the multi-CTA write-back, ns since CTA 0's entry (UpdateArgs::stamps)
+    for (int i = 0; i < 5; i++) out_ns[31 + i] = t[3 + i] > t[0] ? t[3 + i] - t[0] : 0;
+    if (getenv("B2RL_WB_FINE")) { // dev: finer stamps of CTA 0's subtree phase
+        unsigned long long f[3];
+        B2RL_CUDA(cudaMemcpy(f, h->times_dev + 200, sizeof f, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 3; i++) out_ns[28 + i] = f[i] > t[0] ? f[i] - t[0] : 0;
+    }
     return B2RL_OK;
 }

@@ -742,7 +742,21 @@ struct UpdateArgs {
     int nranges;            // 0: normal write-back
     int r_first[4], r_count[4];
     long long bump_n, capacity;
+    // measurement aid (b2rl_step_times [4..8]): %globaltimer stamps of the multi-CTA
+    // write-back -- [0] CTA 0 collected its entries, [1] CTA 0 stored its subtree,
+    // [2] CTA 0 has its arrival ticket, [3] last CTA holds the subtree roots,
+    // [4] last CTA released the completion flag.  NULL: none.
+    unsigned long long *stamps;
 };
+
+__device__ __forceinline__ void upd_stamp(const UpdateArgs &a, int slot)
+{
+    if (a.stamps) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.stamps[slot] = t;
+    }
+}
 
 __host__ __device__ inline size_t update_paths_smem_bytes(int levels)
 {
@@ -963,6 +977,7 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
         }
         __syncthreads();
         const int cnt = ctr[0];
+        if (blockIdx.x == 0 && tid == 0 && st == 0) upd_stamp(a, 0);
         if (cnt == 0) continue; // uniform
         // A subtree usually gets a handful of the 512 leaves: one warp then does the rest
         // with warp barriers only (no 512-thread barrier per level); a crowded subtree
@@ -1022,6 +1037,7 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
                 }
             }
             TEAM_SYNC();
+            if (blockIdx.x == 0 && wt == 0) upd_stamp(a, 197);
             // ---- leaves out, every sibling of every path inside the subtree in
             if (a.nranges == 0)
                 for (int i = wt; i < m; i += wn) {
@@ -1036,10 +1052,21 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
                 sib_m[(size_t)s * UPD_MAX + i] = a.mn[node ^ 1];
             }
             TEAM_SYNC();
-            // ---- level loop on shared memory (see tree_update_paths)
+            if (blockIdx.x == 0 && wt == 0) upd_stamp(a, 198);
+            // ---- level loop on shared memory (see tree_update_paths).  The node values go to
+            // global memory AFTER the loop, in one batch, so that no global store sits in front
+            // of a level's barrier; the results are parked in the sibling slots (level s, entry i)
+            // they were computed from, -1 marks the entries that wrote nothing at that level
+            // (node sums are never negative).  Measured (b2rl_step_times, B2RL_WB_FINE=1): the
+            // loop still costs ~0.4 us per level -- a chain of dependent shared-memory loads
+            // behind the previous level's stores -- 5.5 of the write-back's 19 us.
             for (int s = 0; s < lb; s++) {
                 for (int i = wt; i < m; i += wn) {
-                    if (!lead[i]) continue;
+                    const size_t slot = (size_t)s * UPD_MAX + i;
+                    if (!lead[i]) {
+                        sib_s[slot] = -1.0;
+                        continue;
+                    }
                     const long long node = (a.nslots + leaf[i]) >> s;
                     double ns, nm;
                     if ((node & 1) == 0) {
@@ -1049,29 +1076,40 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
                             nm = fmin(vm[i], vm[j]);
                             runlen[i] += runlen[j];
                         } else {
-                            ns = __dadd_rn(vs[i], sib_s[(size_t)s * UPD_MAX + i]);
-                            nm = fmin(vm[i], sib_m[(size_t)s * UPD_MAX + i]);
+                            ns = __dadd_rn(vs[i], sib_s[slot]);
+                            nm = fmin(vm[i], sib_m[slot]);
                         }
                     } else {
                         if (i > 0 && ((a.nslots + leaf[i - 1]) >> s) == node - 1) {
                             lead[i] = 0;
+                            sib_s[slot] = -1.0;
                             continue;
                         }
-                        ns = __dadd_rn(sib_s[(size_t)s * UPD_MAX + i], vs[i]);
-                        nm = fmin(sib_m[(size_t)s * UPD_MAX + i], vm[i]);
+                        ns = __dadd_rn(sib_s[slot], vs[i]);
+                        nm = fmin(sib_m[slot], vm[i]);
                     }
                     vs[i] = ns;
                     vm[i] = nm;
-                    a.sum[node >> 1] = ns;
-                    a.mn[node >> 1] = nm;
+                    sib_s[slot] = ns;
+                    sib_m[slot] = nm;
                 }
                 TEAM_SYNC();
             }
+            for (int idx = wt; idx < m * lb; idx += wn) {
+                const int i = idx % m, s = idx / m;
+                const double ns = sib_s[(size_t)s * UPD_MAX + i];
+                if (ns < 0.0) continue;
+                const long long parent = (a.nslots + leaf[i]) >> (s + 1);
+                a.sum[parent] = ns;
+                a.mn[parent] = sib_m[(size_t)s * UPD_MAX + i];
+            }
+            if (blockIdx.x == 0 && wt == 0) upd_stamp(a, 199);
         }
 #undef TEAM_SYNC
         __syncthreads(); // the team rejoins the CTA (uniform: cnt is the same for all)
     }
     // ---- max_priority (positive doubles order like their bit patterns), arrival
+    if (blockIdx.x == 0 && tid == 0) upd_stamp(a, 1);
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     __threadfence(); // this thread's node stores before the CTA's arrival ticket
     __syncthreads();
@@ -1085,6 +1123,7 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
         __threadfence();
         const unsigned prev = atomicInc(reinterpret_cast<unsigned *>(sync + 1), gridDim.x - 1);
         ctr[1] = (prev == gridDim.x - 1);
+        if (blockIdx.x == 0) upd_stamp(a, 2);
     }
     __syncthreads();
     if (ctr[1]) {
@@ -1095,6 +1134,7 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
             t_min[NS + i] = __ldcg(a.mn + NS + i);
         }
         __syncthreads();
+        if (tid == 0) upd_stamp(a, 3);
         for (int lv = sl - 1; lv >= 0; lv--) {
             const int w = 1 << lv;
             for (int i = tid; i < w; i += nt) {
@@ -1122,6 +1162,7 @@ __device__ __forceinline__ void tree_update_multi(const UpdateArgs &a, unsigned 
         __threadfence();
         __syncthreads();
         if (tid == 0) st_release_gpu(sync, seq);
+        if (tid == 0) upd_stamp(a, 4);
     }
 }
 
