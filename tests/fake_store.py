@@ -117,6 +117,24 @@ class OracleBackedStore(FakeStore):
         self.max_priority = self.tree.max_priority
         self._last_idx = None
 
+    def update_host_errors(self, errors, alpha, eps, error_min, error_max, defer):
+        """The product path of update_errors(host list): the priorities come from the LIBRARY's
+        host arithmetic (b2rl_host_priority_from_errors, libm pow) -- so the CPU replays of the
+        reference's golden traces also pin that arithmetic, not only the Python formula."""
+        import ctypes
+
+        from pfrl_b200 import _lib
+
+        e = np.ascontiguousarray(errors, dtype=np.float64)
+        out = np.empty_like(e)
+        _lib.check(_lib.load().b2rl_host_priority_from_errors(
+            e.ctypes.data_as(ctypes.c_void_p), e.shape[0], float(alpha), float(eps),
+            int(error_min is not None), 0.0 if error_min is None else float(error_min),
+            int(error_max is not None), 0.0 if error_max is None else float(error_max),
+            out.ctypes.data_as(ctypes.c_void_p)))
+        assert (out > 0.0).all()  # collections/prioritized.py:109
+        self.update_priorities(out)
+
     def read_priorities(self, first=0, n=None):
         n = len(self.records) - first if n is None else n
         return np.array([r["priority"] for r in self.records[first:first + n]], dtype=np.float64)
